@@ -1,0 +1,109 @@
+/*
+ * pixelsynth_b200.h -- C ABI of libpixelsynth_b200.so (sm_100a CUDA kernels for the PixelSynth
+ * novel-view-synthesis inference hot path).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; tensors are dense, row-major,
+ *     in the layouts the reference's PyTorch code uses (NCHW float32 unless stated);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued
+ *     on it, nothing synchronises the device and nothing allocates: the caller owns every buffer,
+ *     including the scratch `workspace` whose size the matching *_workspace_bytes() call returns;
+ *   - return value: PS_OK (0) or a negative PS_E* code; ps_error_string() names it and
+ *     ps_last_error_detail() gives the thread-local detail (e.g. the CUDA error string);
+ *   - inputs are never written.  Re-entrant across host threads / devices: no mutable global state.
+ *
+ * Each entry point cites the reference interface (crockwell/pixelsynth @ cfe18078) it replaces.
+ */
+#ifndef PIXELSYNTH_B200_H_
+#define PIXELSYNTH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_OK 0
+#define PS_EINVAL (-1)       /* bad argument (shape, null pointer, unsupported value) */
+#define PS_ECUDA (-2)        /* a CUDA runtime call or kernel launch failed */
+#define PS_EWORKSPACE (-3)   /* workspace too small */
+#define PS_EUNSUPPORTED (-4) /* valid in the reference but not built here (e.g. K > PS_MAX_POINTS_PER_PIXEL) */
+
+#define PS_ABI_VERSION 1
+/* PyTorch3D's kMaxPointsPerPixel is 150; the reference uses pp_pixel = 128 (options/train_options.py:104). */
+#define PS_MAX_POINTS_PER_PIXEL 128
+
+#define PS_ACCUM_ALPHACOMPOSITE 0
+#define PS_ACCUM_WSUM 1
+#define PS_ACCUM_WSUMNORM 2
+
+int ps_abi_version(void);
+const char* ps_error_string(int code);
+const char* ps_last_error_detail(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Splat stage 1-2: unproject the source pixel grid with depth, camera-transform, perspective divide.
+ * Replaces PtsManipulator.project_pts (models/projection/z_buffer_manipulator.py:50-83) including the
+ * `xyzs` grid buffer of PtsManipulator.__init__ (:38-48).
+ *   depth  (B, W*W)   source depth, pixel order p = y*W + x            [pred_pts.view(bs,1,-1)]
+ *   mats   (B, 6, 16) row-major 4x4 [K, Kinv, RT1, RT1inv, RT2, RT2inv] (forward_justpts order, :85-87)
+ *   pts    (B, W*W, 3) out: `sampler` permuted point-major (as at :103): x right, y down, z>0 in front;
+ *                      points with |z_proj| < eps are parked at (-10, 10, 10)
+ *   xyproj (B, 4, W*W) out or NULL: pre-division homogeneous coords, the cloud that
+ *                      project_pts_cumulative returns (:266)
+ * ------------------------------------------------------------------------------------------------ */
+int ps_project_pts(const float* depth, const float* mats, int B, int W, float eps, float* pts, float* xyproj,
+                   void* stream);
+
+/* Prior-cloud branch of PtsManipulator.project_pts_cumulative (z_buffer_manipulator.py:244-248,253-264).
+ *   cloud (B,4,P) homogeneous points in the previous target camera frame; mats3 (B,3,16) = [K, RT2, RT3inv]. */
+int ps_project_cloud(const float* cloud, const float* mats3, int B, int P, float eps, float* pts, float* xyproj,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Splat stage 3-5: K-nearest z-buffer rasterisation + alpha + accumulate + background mask.
+ * Replaces RasterizePointsXYsBlending.forward (models/layers/z_buffer_layers.py:55-131), i.e.
+ * pytorch3d rasterize_points (:81-84), the alpha formula (:89-98), the 13x13 background dilation
+ * (:100-110) and pytorch3d compositing.{alpha_composite,weighted_sum,weighted_sum_norm} (:112-129).
+ *   pts    (B,P,3) point cloud in project_pts' frame (NOT yet negated; the kernel applies :71-72)
+ *   feat   (B,C,P) per-point features (`src`)
+ *   S      output image side; K = points_per_pixel (<= PS_MAX_POINTS_PER_PIXEL)
+ *   radius_px = opt.radius (pixels); the NDC radius is radius_px / S * 2 as at :77
+ *   out     (B,C,S,S) f32                       [transformed_src_alphas]
+ *   bg_mask (B,S,S)   u8 0/1                    [background_mask]
+ *   idx     (B,S,S,K) i32 packed b*P+p or -1    [rasterize_points()[0]]   may be NULL
+ *   zbuf    (B,S,S,K) f32 or -1                 [rasterize_points()[1]]   may be NULL
+ *   dist2   (B,S,S,K) f32 or -1                 [rasterize_points()[2]]   may be NULL
+ * Selection is ascending (z, packed index); membership is z >= 0 and dx*dx + dy*dy < r*r evaluated in
+ * fp32 without FMA contraction; no point is ever dropped for capacity reasons.
+ * ------------------------------------------------------------------------------------------------ */
+size_t ps_splat_workspace_bytes(int B, int P, int S, double radius_px);
+int ps_splat_points(const float* pts, const float* feat, int B, int P, int C, int S, int K, double radius_px,
+                    double tau, int rad_pow, int accumulation, int bg_ksize, float* out, uint8_t* bg_mask,
+                    int32_t* idx, float* zbuf, float* dist2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* forward_justpts (z_buffer_manipulator.py:85-107) = ps_project_pts + ps_splat_points with P = W*W.
+ * The projected cloud lives in the workspace (ps_splat_fwd_workspace_bytes). */
+size_t ps_splat_fwd_workspace_bytes(int B, int W, int S, double radius_px);
+int ps_splat_fwd(const float* depth, const float* feat, const float* mats, int B, int W, int C, int S, int K,
+                 double radius_px, double tau, int rad_pow, int accumulation, int bg_ksize, float eps, float* out,
+                 uint8_t* bg_mask, int32_t* idx, float* zbuf, float* dist2, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Number of kernels this library has launched from the calling thread since the last reset
+ * (bench.py's `gpu_launches`). */
+long long ps_launch_count(void);
+void ps_launch_count_reset(void);
+
+/* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels (currently
+ * "fine_kernel") are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
+ * synchronises those events and returns the summed duration and launch count for `name`;
+ * ps_timing_collect(NULL, ...) returns the sum over all names and releases the events. */
+void ps_timing_enable(int on);
+int ps_timing_collect(const char* kernel, double* total_ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELSYNTH_B200_H_ */

@@ -1,0 +1,154 @@
+"""Generates tests/golden/splat_*.npz by running the REFERENCE's own splat glue on CPU.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_splat_golden.py
+
+What runs unmodified from /root/reference:
+  models/projection/z_buffer_manipulator.py  PtsManipulator.__init__ (xyzs grid), project_pts, forward_justpts
+  models/layers/z_buffer_layers.py           RasterizePointsXYsBlending.forward (negation, radius, alpha
+                                             formula, permutes, 13x13 background dilation, compositor call)
+What is substituted (absent third-party dependency, PyTorch3D 0.4.0 / 0.2.0@e3819a49, docs/INSTALL.md:11,59,74):
+  pytorch3d.structures.Pointclouds, pytorch3d.renderer.points.rasterize_points,
+  pytorch3d.renderer.compositing.alpha_composite|weighted_sum|weighted_sum_norm
+  -> oracle.splat_ref.np_rasterize_points / np_alpha_composite (numpy brute force of the published
+     algorithm).  `Tensor.cuda()` is patched to a no-op (z_buffer_layers.py:107).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import splat_ref  # noqa: E402
+
+REF = "/root/reference"
+CAPTURE = {}
+
+
+class _Pointclouds:
+    def __init__(self, points, features=None):
+        self._points = points
+        self._features = features
+
+    def points_padded(self):
+        return self._points
+
+    def features_packed(self):
+        f = self._features
+        return f.reshape(-1, f.shape[-1])
+
+
+def _rasterize_points(pointclouds, image_size=256, radius=0.01, points_per_pixel=8, bin_size=None,
+                      max_points_per_bin=None):
+    pts = pointclouds.points_padded().detach().cpu().numpy()
+    idx, zbuf, d2 = splat_ref.np_rasterize_points(pts, image_size, radius, points_per_pixel)
+    CAPTURE["idx"], CAPTURE["zbuf"], CAPTURE["dist2"] = idx.astype(np.int32), zbuf, d2
+    return torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(zbuf), torch.from_numpy(d2)
+
+
+def _alpha_composite(pointsidx, alphas, pt_clds):
+    return torch.from_numpy(splat_ref.np_alpha_composite(pointsidx.numpy(), alphas.numpy(), pt_clds.numpy()))
+
+
+def _weighted_sum(pointsidx, alphas, pt_clds, norm=False):
+    i = pointsidx.numpy()
+    a = np.where(i >= 0, alphas.numpy(), 0).astype(np.float32)
+    f = pt_clds.numpy()[:, np.where(i >= 0, i, 0)]  # (C,N,K,H,W)
+    out = (f * a[None]).sum(2, dtype=np.float32).transpose(1, 0, 2, 3)
+    if norm:
+        out = out / np.maximum(a.sum(1, dtype=np.float32), np.float32(1e-4))[:, None]
+    return torch.from_numpy(np.ascontiguousarray(out, np.float32))
+
+
+def install_stubs():
+    p3d = types.ModuleType("pytorch3d")
+    st = types.ModuleType("pytorch3d.structures")
+    st.Pointclouds = _Pointclouds
+    rd = types.ModuleType("pytorch3d.renderer")
+    comp = types.ModuleType("pytorch3d.renderer.compositing")
+    comp.alpha_composite = _alpha_composite
+    comp.weighted_sum = lambda i, a, f: _weighted_sum(i, a, f, False)
+    comp.weighted_sum_norm = lambda i, a, f: _weighted_sum(i, a, f, True)
+    rp = types.ModuleType("pytorch3d.renderer.points")
+    rp.rasterize_points = _rasterize_points
+    rd.compositing = comp
+    rd.points = rp
+    for name, mod in (("pytorch3d", p3d), ("pytorch3d.structures", st), ("pytorch3d.renderer", rd),
+                      ("pytorch3d.renderer.compositing", comp), ("pytorch3d.renderer.points", rp)):
+        sys.modules[name] = mod
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    os.environ["DEBUG"] = "False"
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+def cameras(B, rng, kind):
+    """demo.py:36-96 camera (offset * origK, identity extrinsics) and a target pose."""
+    offset = np.array([[2, 0, -1], [0, -2, 1], [0, 0, -1]], np.float32)
+    origK = np.array([[1, 0, .5], [0, 1, .5], [0, 0, 1]], np.float32)
+    P = np.eye(4, dtype=np.float32)
+    P[:3, :3] = offset @ origK
+    Pinv = np.linalg.inv(P).astype(np.float32)
+    K = np.eye(4, dtype=np.float32)
+    RT1 = np.repeat(P[None], B, 0)
+    RT1inv = np.repeat(Pinv[None], B, 0)
+    RT2 = RT1.copy()
+    for b in range(B):
+        if kind == "translate":  # z_buffermodel.py:214 circle translation
+            n = rng.integers(0, 8)
+            RT2[b, :3, 3] += (.35 * np.array([np.sin(2 * np.pi * n / 8), np.cos(2 * np.pi * n / 8),
+                                              .4 * np.sin(2 * np.pi * (.25 + n / 8))])).astype(np.float32)
+        elif kind == "rotate":  # z_buffermodel.py:229-240, direction L, rotation .6
+            th = -0.6 * (b + 1) / B
+            M = np.eye(4, dtype=np.float32)
+            M[0, 0] = np.cos(th); M[0, 2] = np.sin(th); M[2, 0] = -np.sin(th); M[2, 2] = np.cos(th)
+            RT2[b] = M @ RT1[b]
+        elif kind == "behind":  # push some points behind the camera / onto the EPS plane
+            RT2[b, 2, 3] += 2.0
+    RT2inv = np.linalg.inv(RT2).astype(np.float32)
+    Ks = np.repeat(K[None], B, 0)
+    return Ks, Ks.copy(), RT1, RT1inv, RT2, RT2inv
+
+
+def run_case(name, W, K, radius_px, kind, B=2, C=3, tau=1.0, accumulation="alphacomposite", ksize=13, seed=0,
+             depth_mode="uniform"):
+    from models.projection.z_buffer_manipulator import PtsManipulator
+    rng = np.random.default_rng(seed)
+    opt = types.SimpleNamespace(splatter="xyblending", learn_default_feature=True, radius=radius_px, pp_pixel=K,
+                                rad_pow=2, tau=tau, accumulation=accumulation, background_smoothing_kernel_size=ksize)
+    torch.manual_seed(0)
+    pm = PtsManipulator(W, C=C, opt=opt)
+    if depth_mode == "uniform":
+        depth = rng.uniform(0.5, 10.0, (B, 1, W, W)).astype(np.float32)
+    elif depth_mode == "const":  # all-equal z: ordering is pure tie-break
+        depth = np.full((B, 1, W, W), 2.0, np.float32)
+    else:  # quantised: many exact z ties
+        depth = (np.round(rng.uniform(0.5, 4.0, (B, 1, W, W)) * 4) / 4).astype(np.float32)
+    feat = rng.uniform(-1, 1, (B, C, W, W)).astype(np.float32)
+    mats = cameras(B, rng, kind)
+    t = [torch.from_numpy(m) for m in mats]
+    with torch.no_grad():
+        pts = pm.project_pts(torch.from_numpy(depth).view(B, 1, -1), *t)
+        gen_fs, bg = pm.forward_justpts(torch.from_numpy(feat), torch.from_numpy(depth), *t)
+    out = dict(depth=depth, feat=feat, mats=splat_ref.pack_mats(*mats), W=W, K=K, radius_px=radius_px, tau=tau,
+               ksize=ksize, accumulation=accumulation, xyzs=pm.xyzs.numpy(),
+               ref_pts=pts.permute(0, 2, 1).contiguous().numpy(), ref_gen_fs=gen_fs.numpy(), ref_bg=bg.numpy(),
+               idx=CAPTURE["idx"], zbuf=CAPTURE["zbuf"], dist2=CAPTURE["dist2"])
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), f"splat_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(name, "pts", out["ref_pts"].shape, "hits/pixel mean", (out["idx"] >= 0).sum(-1).mean(),
+          "empty", (out["idx"][..., 0] < 0).mean(), os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    install_stubs()
+    run_case("w32_k8_translate", 32, 8, 4.0, "translate")
+    run_case("w32_k64_rotate", 32, 64, 2.0, "rotate")
+    run_case("w32_k16_behind", 32, 16, 4.0, "behind")
+    run_case("w32_k32_ties", 32, 32, 4.0, "identity", depth_mode="const")
+    run_case("w32_k32_quant", 32, 32, 4.0, "translate", depth_mode="quant")
+    run_case("w32_k16_wsum", 32, 16, 3.0, "translate", accumulation="wsum", tau=2.0, ksize=5)
+    run_case("w32_k16_wsumnorm", 32, 16, 3.0, "rotate", accumulation="wsumnorm")
+    run_case("w48_k128_translate", 48, 128, 4.0, "translate", B=1)

@@ -6,16 +6,16 @@
 //   PyTorch3D rasterize_points + compositing (not vendored; semantics in SURVEY.md Appendix A)
 //
 // Design (HBM-bound: 69.0 MB of mandatory output per 256x256 view when the idx/z maps are emitted):
-//   1. bin_count / scan / bin_fill : every point is appended to the candidate list of each 8x8-pixel
-//      tile its disc can touch (conservative box, +1 px margin).  Lists hold point ids only.
-//   2. fine_kernel, one 64-thread CTA per tile: candidates are sorted ONCE per tile by the canonical
-//      key (z, point id) in shared memory; each thread then walks the sorted list for its pixel, so a
-//      pixel's hits come out already in output order and no per-pixel sort or heap is needed.  A second
-//      phase gives one warp lane to each output slot: alpha, transmittance prefix product, weighted
-//      feature sum, and 512-byte coalesced row stores of idx / zbuf / dist2.
-//   3. tiles whose list exceeds the shared-memory capacity are queued and handled by fine_big_kernel,
-//      which streams the list in sorted chunks and merges into a per-pixel running top-K, so no point
-//      is ever dropped (PyTorch3D's binned path silently drops on bin overflow).
+//   1. bin_kernel (projection fused in): every point is appended, with warp-aggregated atomics, to the
+//      fixed-capacity candidate list of each 8x8-pixel tile its disc can reach (tight, conservative box).
+//   2. fine_kernel, one 64-thread CTA per tile: candidates are sorted ONCE per tile by the canonical key
+//      (z, point id) with a shared-memory counting sort; warps then ballot the exact membership test of 32
+//      sorted candidates against the tile's 64 pixels, so every pixel's hits come out already in output
+//      order as bit masks; one thread per pixel expands its masks and composites front to back; finally
+//      each warp streams a pixel's K slots of idx / zbuf / dist2 with 16-byte coalesced stores.
+//   3. tiles with more candidates than the shared-memory capacity are queued for fine_big_kernel, which
+//      streams the list (or, if even the list overflowed, the whole cloud) in sorted chunks and merges into a
+//      per-pixel running top-K, so no point is ever dropped (PyTorch3D's binned path drops on bin overflow).
 //   4. bgmask_kernel: separable k x k box dilation of the "pixel received no point" map.
 //
 // Bit-exact surfaces (idx, zbuf, dist2, pts) use __f*_rn intrinsics so ptxas never contracts to FMA;
@@ -25,11 +25,15 @@
 namespace ps {
 
 constexpr int TILE = 8;
-constexpr int FINE_THREADS = TILE * TILE;
-constexpr int CAP = 512;    // candidates per tile handled by the shared-memory fast path
-constexpr int CAPB = 1024;  // chunk size of the overflow path
+constexpr int TPB = TILE * TILE;  // threads per tile CTA
+constexpr int CAP = 512;          // candidates per tile handled by the shared-memory fast path
+constexpr int CAPG = 1024;        // capacity of a tile's candidate list in global memory
+constexpr int CAPB = 1024;        // chunk size of the overflow path
+constexpr int NB = 1024;          // buckets of the per-tile counting sort
+constexpr int MAXBK = 32;         // largest bucket ranked by comparison; beyond that the tile is bitonic-sorted
 constexpr int MAXK = PS_MAX_POINTS_PER_PIXEL;
-constexpr int MAXC_SMEM = 4;  // feature channels cached in shared memory by the fast path
+constexpr int LSTRIDE = MAXK + 4;    // u16 per pixel row of the slot lists (8-byte aligned rows)
+constexpr int BSTRIDE = CAP / 32 + 1;  // words per pixel row of the hit masks (odd: conflict-free columns)
 constexpr unsigned FULL = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
@@ -149,26 +153,29 @@ __global__ void __launch_bounds__(256) project_cloud_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 3a: binning
+// stage 3a: binning.  One pass: every point is appended (warp-aggregated atomics) to the fixed-capacity
+// candidate list of each 8x8-pixel tile whose pixels its disc can reach.  tile_count keeps the true
+// number of candidates even when it exceeds the list capacity, so nothing is dropped silently: such
+// tiles are re-derived from the whole cloud by fine_big_kernel.
 // ------------------------------------------------------------------------------------------------
 struct BinGeom {
   int S, nt;     // image side, tiles per side
   float half_S;  // S/2
-  float rp;      // radius in pixels + 1 px safety margin
+  float rp;      // radius in pixels + 1/64 px (covers the fp32 error of the pixel-coordinate estimate)
   float lim;     // |x| beyond this can never touch the image
 };
 
-// Conservative set of tiles a point's disc can touch.  Every pixel that passes the exact test
-// (z >= 0, dx*dx+dy*dy < r*r) lies inside this box; the box may contain pixels that fail it.
-__device__ __forceinline__ bool tile_range(const float* __restrict__ pt, const BinGeom& g, int& tx0, int& tx1, int& ty0,
+// Tile range of the pixel columns/rows a point can reach.  A pixel passes the exact test only if
+// |dx| < r(1+2^-22) and |dy| < r(1+2^-22) (dx*dx <= dx*dx+dy*dy under round-to-nearest), i.e. its index lies
+// within radius_px(1+2^-21) + S*2^-22 of the point's pixel coordinate; rp adds 1/64 px on top of radius_px.
+__device__ __forceinline__ bool tile_range(float x, float y, float z, const BinGeom& g, int& tx0, int& tx1, int& ty0,
                                            int& ty1) {
-  const float x = pt[0], y = pt[1], z = pt[2];
-  if (!(z >= 0.0f)) return false;
+  if (!(z >= 0.0f)) return false;                                           // behind the camera, or NaN
   if (!(x > -g.lim && x < g.lim && y > -g.lim && y < g.lim)) return false;  // also rejects NaN
   const float fx = (x + 1.0f) * g.half_S - 0.5f;
   const float fy = (y + 1.0f) * g.half_S - 0.5f;
-  int x0 = (int)floorf(fx - g.rp), x1 = (int)ceilf(fx + g.rp);
-  int y0 = (int)floorf(fy - g.rp), y1 = (int)ceilf(fy + g.rp);
+  int x0 = (int)ceilf(fx - g.rp), x1 = (int)floorf(fx + g.rp);
+  int y0 = (int)ceilf(fy - g.rp), y1 = (int)floorf(fy + g.rp);
   x0 = max(x0, 0);
   y0 = max(y0, 0);
   x1 = min(x1, g.S - 1);
@@ -181,111 +188,116 @@ __device__ __forceinline__ bool tile_range(const float* __restrict__ pt, const B
   return true;
 }
 
-__global__ void __launch_bounds__(256) bin_count_kernel(const float* __restrict__ pts, int P, BinGeom g,
-                                                        int* __restrict__ tile_count) {
-  const int b = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  int tx0, tx1, ty0, ty1;
-  if (!tile_range(pts + ((size_t)b * P + p) * 3, g, tx0, tx1, ty0, ty1)) return;
-  int* tc = tile_count + (size_t)b * g.nt * g.nt;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tc + ty * g.nt + tx, 1);
-}
+struct ProjectArgs {
+  const float* depth;  // (B,P) when projecting in-kernel
+  const float* mats;   // (B,6,16)
+  int W;
+  float eps;
+};
 
-// one CTA per view: exclusive scan of the view's tile counts; counts are zeroed for reuse as cursors
-__global__ void __launch_bounds__(1024) bin_scan_kernel(int* __restrict__ tile_count, int* __restrict__ tile_start,
-                                                        int nt2) {
-  __shared__ int warp_sums[32];
-  __shared__ int carry_s;
-  const int b = blockIdx.x;
-  int* tc = tile_count + (size_t)b * nt2;
-  int* ts = tile_start + (size_t)b * nt2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < nt2; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = (i < nt2) ? tc[i] : 0;
-    int incl = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int t = __shfl_up_sync(FULL, incl, off);
-      if (lane >= off) incl += t;
+// PROJECT: points are produced here from depth (project_pts fused in); otherwise read from pts (B,P,3).
+// Either way a 16-byte-aligned copy (x, y, z, 0) goes to pts4 for the tile kernels.
+template <bool PROJECT>
+__global__ void __launch_bounds__(256) bin_kernel(ProjectArgs pa, const float* __restrict__ pts, int P, BinGeom g,
+                                                  float4* __restrict__ pts4, int* __restrict__ tile_count,
+                                                  int* __restrict__ list) {
+  __shared__ float sK[16], sKinv[16], sRT[16];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  if (PROJECT) {
+    const float* m = pa.mats + (size_t)b * 96;
+    if (threadIdx.x < 16) {
+      sK[threadIdx.x] = m[threadIdx.x];
+      sKinv[threadIdx.x] = m[16 + threadIdx.x];
+      matmul4_entry(m + 64, m + 48, sRT, threadIdx.x);  // RT = RT2 * RT1inv
     }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int ws = warp_sums[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(FULL, ws, off);
-        if (lane >= off) ws += t;
-      }
-      warp_sums[lane] = ws;  // inclusive
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    const int woff = (warp == 0) ? 0 : warp_sums[warp - 1];
-    if (i < nt2) {
-      ts[i] = carry + woff + incl - v;
-      tc[i] = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + warp_sums[31];
     __syncthreads();
   }
-}
-
-__global__ void __launch_bounds__(256) bin_fill_kernel(const float* __restrict__ pts, int P, BinGeom g,
-                                                       int* __restrict__ tile_count, const int* __restrict__ tile_start,
-                                                       int* __restrict__ list, long long cap_per_view) {
-  const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  int tx0, tx1, ty0, ty1;
-  if (!tile_range(pts + ((size_t)b * P + p) * 3, g, tx0, tx1, ty0, ty1)) return;
+  float o[3] = {0.f, 0.f, -1.f};
+  if (p < P) {
+    if (PROJECT) {
+      const int W = pa.W;
+      const int sy = p / W, sx = p - sy * W;
+      const float d = pa.depth[(size_t)b * P + p];
+      const float X0 = __fmul_rn(grid_coord(sx, W), d);
+      const float X1 = __fmul_rn(-grid_coord(sy, W), d);
+      const float X2 = -d;
+      float c[4], w[4], q[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) c[r] = dot4(sKinv + 4 * r, X0, X1, X2, 1.0f);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) w[r] = dot4(sRT + 4 * r, c[0], c[1], c[2], c[3]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) q[r] = dot4(sK + 4 * r, w[0], w[1], w[2], w[3]);
+      finish_point(q[0], q[1], q[2], pa.eps, o);
+    } else {
+      const float* pt = pts + ((size_t)b * P + p) * 3;
+      o[0] = pt[0];
+      o[1] = pt[1];
+      o[2] = pt[2];
+    }
+    pts4[(size_t)b * P + p] = make_float4(o[0], o[1], o[2], 0.0f);
+  }
+  int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+  const bool ok = (p < P) && tile_range(o[0], o[1], o[2], g, tx0, tx1, ty0, ty1);
+  const int ntx = ok ? tx1 - tx0 + 1 : 0;
+  const int ntiles = ok ? ntx * (ty1 - ty0 + 1) : 0;
+  const int maxt = __reduce_max_sync(FULL, ntiles);
   const int nt2 = g.nt * g.nt;
   int* tc = tile_count + (size_t)b * nt2;
-  const int* ts = tile_start + (size_t)b * nt2;
-  int* lst = list + (size_t)b * cap_per_view;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) {
-      const int t = ty * g.nt + tx;
-      const int slot = atomicAdd(tc + t, 1);
-      lst[ts[t] + slot] = p;
+  for (int k = 0; k < maxt; ++k) {
+    const bool has = k < ntiles;
+    int t = -1 - lane;  // unique per lane: forms a singleton group
+    if (has) {
+      const int dy = k / ntx;
+      t = (ty0 + dy) * g.nt + tx0 + (k - dy * ntx);
     }
+    const unsigned grp = __match_any_sync(FULL, t);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (has && lane == leader) base = atomicAdd(tc + t, __popc(grp));
+    base = __shfl_sync(FULL, base, leader);
+    if (has) {
+      const int slot = base + __popc(grp & ((1u << lane) - 1u));
+      if (slot < CAPG) list[((size_t)b * nt2 + t) * CAPG + slot] = p;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // stage 3b-4: per-tile fine rasterisation + compositing
 // ------------------------------------------------------------------------------------------------
 struct FineParams {
-  const float* pts;   // (B,P,3)
-  const float* feat;  // (B,C,P)
+  const float4* pts4;  // (B,P) x, y, z, 0 in project_pts' frame
+  const float* feat;   // (B,C,P)
   const int* tile_count;
-  const int* tile_start;
-  const int* list;
-  long long cap_per_view;
+  const int* list;  // (B, nt2, CAPG)
   int P, C, S, K, nt;
-  float r2;     // (float)radius * (float)radius
-  float denom;  // (float)pow(radius, rad_pow)
+  float r2;         // (float)radius * (float)radius
+  float denom;      // (float)pow(radius, rad_pow)
+  float inv_denom;  // 1/denom when that is exact (denom a power of two), else 0
   float tau;
   int accumulation;
-  float* out;        // (B,C,S,S)
-  uint8_t* empty;    // (B,S,S) 1 where the pixel received no point
-  int32_t* idx;      // (B,S,S,K) or null
-  float* zbuf;       // (B,S,S,K) or null
-  float* dist2;      // (B,S,S,K) or null
-  int* ovf_count;    // tiles that exceeded CAP
+  BinGeom g;       // for the whole-cloud rescan of tiles whose list overflowed
+  float* out;      // (B,C,S,S)
+  uint8_t* empty;  // (B,S,S) 1 where the pixel received no point
+  int32_t* idx;    // (B,S,S,K) or null
+  float* zbuf;     // (B,S,S,K) or null
+  float* dist2;    // (B,S,S,K) or null
+  int* ovf_count;  // tiles that exceeded CAP
   int* ovf_list;
 };
 
-__device__ __forceinline__ float alpha_of(float d2, float denom, float tau) {
-  float d = __fdiv_rn(d2, denom);
+// alpha = (1 - clamp(dist2 / r^rad_pow, 1e-3, 1)^0.5)^tau   (z_buffer_layers.py:89-98).  Feeds only the
+// composited image (tolerance 2e-6), so the square root may be the approximate one.
+__device__ __forceinline__ float alpha_of(float d2, const FineParams& q) {
+  float d = (q.inv_denom != 0.0f) ? d2 * q.inv_denom : __fdiv_rn(d2, q.denom);
   d = fminf(fmaxf(d, 1e-3f), 1.0f);
-  float a = 1.0f - sqrtf(d);
-  if (tau != 1.0f) a = powf(a, tau);
+  float s;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d));
+  float a = 1.0f - s;
+  if (q.tau != 1.0f) a = powf(a, q.tau);
   return a;
 }
 
@@ -307,46 +319,63 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* __restrict_
   }
 }
 
-// Per-warp staging of one pixel's output rows so the global stores are 16-byte vectors.
-struct RowStage {
-  int idx[MAXK];
-  float z[MAXK];
-  float d2[MAXK];
-  float w[MAXK];  // compositing weight per slot (generic-C path)
+struct __align__(16) Cand {
+  float x, y, z;  // x, y already negated (z_buffer_layers.py:71-72)
+  int id;
 };
 
-__device__ __forceinline__ void store_rows(const FineParams& q, const RowStage& st, size_t pixoff, int lane) {
+struct SortScratch {
+  unsigned hist[NB + 2];        // bucket counts -> exclusive starts; hist[NB] = n
+  unsigned long long key[CAP];  // (z bits << 32) | point id, in bucket order
+};
+struct RasterScratch {
+  unsigned bits[TPB][BSTRIDE];         // per pixel: hit mask over the sorted candidates, 32 per word
+  unsigned short lists[TPB][LSTRIDE];  // per pixel: candidate index of output slot k
+};
+struct FineSmem {
+  Cand cand[CAP];
+  float4 feat[CAP];  // up to 4 feature channels of each candidate
+  union {
+    SortScratch s;
+    RasterScratch r;
+  } u;
+  unsigned zmin, zmax, maxcount;
+  unsigned warp_tot[TPB / 32];
+};
+
+// writes the K output slots 4*lane .. 4*lane+3 of one pixel (called by a full warp)
+__device__ __forceinline__ void store_slots(const FineParams& q, size_t pixoff, int lane, const int* id4, const float* z4,
+                                            const float* d4) {
   const int K = q.K;
+  const int k0 = 4 * lane;
+  if (k0 >= K) return;
+  const size_t o = pixoff * K + k0;
   if ((K & 3) == 0) {
-    if (4 * lane < K) {
-      if (q.idx) reinterpret_cast<int4*>(q.idx + pixoff * K)[lane] = reinterpret_cast<const int4*>(st.idx)[lane];
-      if (q.zbuf) reinterpret_cast<float4*>(q.zbuf + pixoff * K)[lane] = reinterpret_cast<const float4*>(st.z)[lane];
-      if (q.dist2) reinterpret_cast<float4*>(q.dist2 + pixoff * K)[lane] = reinterpret_cast<const float4*>(st.d2)[lane];
-    }
+    if (q.idx) __stcs(reinterpret_cast<int4*>(q.idx + o), make_int4(id4[0], id4[1], id4[2], id4[3]));
+    if (q.zbuf) __stcs(reinterpret_cast<float4*>(q.zbuf + o), make_float4(z4[0], z4[1], z4[2], z4[3]));
+    if (q.dist2) __stcs(reinterpret_cast<float4*>(q.dist2 + o), make_float4(d4[0], d4[1], d4[2], d4[3]));
   } else {
-    for (int k = lane; k < K; k += 32) {
-      if (q.idx) q.idx[pixoff * K + k] = st.idx[k];
-      if (q.zbuf) q.zbuf[pixoff * K + k] = st.z[k];
-      if (q.dist2) q.dist2[pixoff * K + k] = st.d2[k];
-    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (k0 + e < K) {
+        if (q.idx) q.idx[o + e] = id4[e];
+        if (q.zbuf) q.zbuf[o + e] = z4[e];
+        if (q.dist2) q.dist2[o + e] = d4[e];
+      }
   }
 }
 
-template <int CAP_>
-struct FineSmem {
-  unsigned long long key[CAP_];
-  float2 xy[CAP_];  // negated coordinates (z_buffer_layers.py:71-72)
-  float z[CAP_];
-  int p[CAP_];
-  float f[MAXC_SMEM][CAP_];
-  unsigned short lists[MAXK][FINE_THREADS];
-  RowStage stage[FINE_THREADS / 32];
-  float col[MAXC_SMEM][FINE_THREADS];
-};
-
-__global__ void __launch_bounds__(FINE_THREADS) fine_kernel(FineParams q) {
+// One 64-thread CTA per 8x8-pixel tile.
+//   A. load the tile's candidates; counting sort by (z, point id): 1024 buckets over the tile's z range,
+//      exact rank inside the (small) buckets; a bitonic sort is the fallback for degenerate z distributions.
+//   B. each warp takes 32 sorted candidates at a time and ballots the exact membership test against the 64
+//      pixels: pixel p gets, per candidate block, a 32-bit hit word whose set bits are already in output order.
+//   C. one thread per pixel expands its hit words into the slot list and composites front to back.
+//   D. one warp per pixel row of K slots: gather (id, z), recompute dist2, 16-byte streaming stores.
+__global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FineSmem<CAP>& sm = *reinterpret_cast<FineSmem<CAP>*>(smem_raw);
+  FineSmem& sm = *reinterpret_cast<FineSmem*>(smem_raw);
+  constexpr int PER = CAP / TPB;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -362,157 +391,298 @@ __global__ void __launch_bounds__(FINE_THREADS) fine_kernel(FineParams q) {
   const int xi = tx * TILE + (tid & 7), yi = ty * TILE + (tid >> 3);
   const bool inimg = xi < S && yi < S;
   const float xf = pix_to_ndc(S - 1 - xi, S), yf = pix_to_ndc(S - 1 - yi, S);
-  const float* ptsb = q.pts + (size_t)b * P * 3;
-  const bool cached = C <= MAXC_SMEM;
 
-  // ---- load candidate keys, sort by (z, point id) ----
-  int N = 2;
-  while (N < n) N <<= 1;
-  const int* lst = q.list + (size_t)b * q.cap_per_view + q.tile_start[(size_t)b * nt2 + t];
-  for (int i = tid; i < N; i += FINE_THREADS) {
-    unsigned long long key = ~0ull;
-    if (i < n) {
-      const int p = lst[i];
-      const float z = ptsb[(size_t)p * 3 + 2] + 0.0f;  // -0 -> +0 so the bit pattern orders like the float
-      key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned)p;
-    }
-    sm.key[i] = key;
+  // ---- A. load + sort ----
+  for (int i = tid; i < NB + 2; i += TPB) sm.u.s.hist[i] = 0;
+  if (tid == 0) {
+    sm.zmin = 0xffffffffu;
+    sm.zmax = 0u;
+    sm.maxcount = 0u;
   }
-  __syncthreads();
-  if (n > 1) bitonic_sort_u64(sm.key, N, tid, FINE_THREADS);
-  for (int i = tid; i < n; i += FINE_THREADS) {
-    const int p = (int)(unsigned)(sm.key[i] & 0xffffffffull);
-    const float* pt = ptsb + (size_t)p * 3;
-    sm.xy[i] = make_float2(-pt[0], -pt[1]);
-    sm.z[i] = pt[2];
-    sm.p[i] = p;
-    if (cached)
-      for (int c = 0; c < C; ++c) sm.f[c][i] = q.feat[((size_t)b * C + c) * P + p];
-  }
-  __syncthreads();
-
-  // ---- phase 1: one thread per pixel walks the sorted candidates; hits come out in output order ----
-  int cnt = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    if (__all_sync(FULL, cnt >= K)) break;
-    const int i1 = min(i0 + 32, n);
-    for (int i = i0; i < i1; ++i) {
-      const float2 c = sm.xy[i];
-      const float d2 = dist2_rn(c.x - xf, c.y - yf);
-      if (d2 < q.r2 && cnt < K) {
-        sm.lists[cnt][tid] = (unsigned short)i;
-        ++cnt;
-      }
-    }
-  }
-  if (inimg) q.empty[((size_t)b * S + yi) * S + xi] = (cnt == 0);
-  __syncwarp();
-
-  // ---- phase 2: one lane per output slot ----
-  RowStage& st = sm.stage[warp];
-  const int rounds = (K + 31) >> 5;
-  const int32_t base = (int32_t)((size_t)b * P);
-  for (int j = 0; j < 32; ++j) {
-    if (!__shfl_sync(FULL, (int)inimg, j)) continue;
-    const int pix = warp * 32 + j;
-    const int nh = __shfl_sync(FULL, cnt, j);
-    const float xfj = __shfl_sync(FULL, xf, j), yfj = __shfl_sync(FULL, yf, j);
-    const int pxi = __shfl_sync(FULL, xi, j), pyi = __shfl_sync(FULL, yi, j);
-    float acc[MAXC_SMEM] = {0.f, 0.f, 0.f, 0.f};
-    float tcarry = 1.0f, wsum = 0.0f;
-    for (int r = 0; r < rounds; ++r) {
-      const int k = r * 32 + lane;
-      const bool valid = k < nh;
-      float a = 0.0f, z = -1.0f, d2 = -1.0f;
-      int pid = -1, ci = 0;
-      if (valid) {
-        ci = sm.lists[k][pix];
-        const float2 c = sm.xy[ci];
-        d2 = dist2_rn(c.x - xfj, c.y - yfj);
-        z = sm.z[ci];
-        pid = base + sm.p[ci];
-        a = alpha_of(d2, q.denom, q.tau);
-      }
-      if (k < K) {
-        st.idx[k] = pid;
-        st.z[k] = z;
-        st.d2[k] = d2;
-      }
-      if (r * 32 >= nh) continue;  // warp-uniform: nothing to composite in this round
-      float wgt;
-      if (q.accumulation == PS_ACCUM_ALPHACOMPOSITE) {
-        float incl = 1.0f - a;  // a == 0 for invalid lanes
+  const int* lst = q.list + ((size_t)b * nt2 + t) * CAPG;
+  const float4* p4 = q.pts4 + (size_t)b * P;
+  int id[PER];
+  float cx[PER], cy[PER], cz[PER];
+  unsigned zb[PER];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const float v = __shfl_up_sync(FULL, incl, off);
-          if (lane >= off) incl *= v;
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + j * TPB;
+    id[j] = (i < n) ? __ldg(lst + i) : 0;
+  }
+  unsigned lmin = 0xffffffffu, lmax = 0u;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + j * TPB;
+    if (i < n) {
+      const float4 v = __ldg(p4 + id[j]);
+      cx[j] = v.x;
+      cy[j] = v.y;
+      cz[j] = v.z;
+      zb[j] = __float_as_uint(v.z + 0.0f);  // -0 -> +0: the bit pattern of z >= 0 orders like the float
+      lmin = min(lmin, zb[j]);
+      lmax = max(lmax, zb[j]);
+    }
+  }
+  lmin = __reduce_min_sync(FULL, lmin);
+  lmax = __reduce_max_sync(FULL, lmax);
+  __syncthreads();
+  if (lane == 0 && n > 0) {
+    atomicMin(&sm.zmin, lmin);
+    atomicMax(&sm.zmax, lmax);
+  }
+  __syncthreads();
+  const unsigned zmin = sm.zmin;
+  const unsigned range = sm.zmax - zmin;
+  const int sh = (n > 0 && range >= (unsigned)NB) ? (32 - __clz(range) - 10) : 0;
+  unsigned bo[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + j * TPB;
+    if (i < n) {
+      const unsigned bk = (zb[j] - zmin) >> sh;
+      bo[j] = (bk << 16) | atomicAdd(&sm.u.s.hist[bk], 1u);
+    }
+  }
+  __syncthreads();
+  {  // exclusive scan of the NB bucket counts; each thread owns NB/TPB consecutive buckets
+    constexpr int BPT = NB / TPB;
+    unsigned v[BPT];
+    unsigned tot = 0, mx = 0;
+#pragma unroll
+    for (int e = 0; e < BPT; e += 4) {
+      const uint4 w = *reinterpret_cast<const uint4*>(&sm.u.s.hist[tid * BPT + e]);
+      v[e] = w.x;
+      v[e + 1] = w.y;
+      v[e + 2] = w.z;
+      v[e + 3] = w.w;
+    }
+#pragma unroll
+    for (int e = 0; e < BPT; ++e) {
+      const unsigned c = v[e];
+      mx = max(mx, c);
+      v[e] = tot;
+      tot += c;
+    }
+    unsigned incl = tot;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned u = __shfl_up_sync(FULL, incl, off);
+      if (lane >= off) incl += u;
+    }
+    mx = __reduce_max_sync(FULL, mx);
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    if (lane == 0) atomicMax(&sm.maxcount, mx);
+    __syncthreads();
+    unsigned base = incl - tot;
+    for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+#pragma unroll
+    for (int e = 0; e < BPT; e += 4)
+      *reinterpret_cast<uint4*>(&sm.u.s.hist[tid * BPT + e]) =
+          make_uint4(base + v[e], base + v[e + 1], base + v[e + 2], base + v[e + 3]);
+    if (tid == 0) sm.u.s.hist[NB] = (unsigned)n;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + j * TPB;
+    if (i < n)
+      sm.u.s.key[sm.u.s.hist[bo[j] >> 16] + (bo[j] & 0xffffu)] =
+          ((unsigned long long)zb[j] << 32) | (unsigned)id[j];
+  }
+  __syncthreads();
+  const float* featb = q.feat + (size_t)b * C * P;
+  if (sm.maxcount <= (unsigned)MAXBK) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = tid + j * TPB;
+      if (i < n) {
+        const unsigned bk = bo[j] >> 16;
+        const unsigned s0 = sm.u.s.hist[bk], c = sm.u.s.hist[bk + 1] - s0;
+        unsigned rank = 0;
+        if (c > 1) {
+          const unsigned long long mine = ((unsigned long long)zb[j] << 32) | (unsigned)id[j];
+          for (unsigned m = 0; m < c; ++m) rank += (sm.u.s.key[s0 + m] < mine) ? 1u : 0u;
         }
-        float excl = __shfl_up_sync(FULL, incl, 1);
-        if (lane == 0) excl = 1.0f;
-        wgt = tcarry * excl * a;
-        tcarry *= __shfl_sync(FULL, incl, 31);
+        const int fin = (int)(s0 + rank);
+        Cand cd;
+        cd.x = -cx[j];
+        cd.y = -cy[j];
+        cd.z = cz[j];
+        cd.id = id[j];
+        sm.cand[fin] = cd;
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        f.x = __ldg(featb + id[j]);
+        if (C > 1) f.y = __ldg(featb + (size_t)P + id[j]);
+        if (C > 2) f.z = __ldg(featb + 2 * (size_t)P + id[j]);
+        if (C > 3) f.w = __ldg(featb + 3 * (size_t)P + id[j]);
+        sm.feat[fin] = f;
+      }
+    }
+  } else {  // degenerate z distribution (e.g. constant depth): full sort of the 64-bit keys
+    int N = 2;
+    while (N < n) N <<= 1;
+    for (int i = n + tid; i < N; i += TPB) sm.u.s.key[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(sm.u.s.key, N, tid, TPB);
+    for (int i = tid; i < n; i += TPB) {
+      const int pid = (int)(unsigned)(sm.u.s.key[i] & 0xffffffffull);
+      const float4 v = __ldg(p4 + pid);
+      Cand cd;
+      cd.x = -v.x;
+      cd.y = -v.y;
+      cd.z = v.z;
+      cd.id = pid;
+      sm.cand[i] = cd;
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      f.x = __ldg(featb + pid);
+      if (C > 1) f.y = __ldg(featb + (size_t)P + pid);
+      if (C > 2) f.z = __ldg(featb + 2 * (size_t)P + pid);
+      if (C > 3) f.w = __ldg(featb + 3 * (size_t)P + pid);
+      sm.feat[i] = f;
+    }
+  }
+  __syncthreads();  // cand/feat complete; sort scratch is dead from here (aliased by bits/lists)
+
+  // ---- B. membership ballots, 32 sorted candidates x 64 pixels per step ----
+  const int nblk = (n + 31) >> 5;
+  {
+    float xfc[TILE], yfr[TILE];
+#pragma unroll
+    for (int c = 0; c < TILE; ++c) {
+      xfc[c] = pix_to_ndc(S - 1 - (tx * TILE + c), S);
+      yfr[c] = pix_to_ndc(S - 1 - (ty * TILE + c), S);
+    }
+    for (int blk = warp; blk < nblk; blk += TPB / 32) {
+      const int ci = blk * 32 + lane;
+      float px = 1e30f, py = 1e30f;  // lanes past the end never hit
+      if (ci < n) {
+        px = sm.cand[ci].x;
+        py = sm.cand[ci].y;
+      }
+      float dx2[TILE], dy2[TILE];
+#pragma unroll
+      for (int c = 0; c < TILE; ++c) {
+        const float dx = __fsub_rn(px, xfc[c]), dy = __fsub_rn(py, yfr[c]);
+        dx2[c] = __fmul_rn(dx, dx);
+        dy2[c] = __fmul_rn(dy, dy);
+      }
+#pragma unroll
+      for (int r = 0; r < TILE; ++r)
+#pragma unroll
+        for (int c = 0; c < TILE; ++c) {
+          const unsigned bal = __ballot_sync(FULL, __fadd_rn(dx2[c], dy2[r]) < q.r2);
+          if (lane == 0) sm.u.r.bits[r * TILE + c][blk] = bal;
+        }
+    }
+  }
+  __syncthreads();
+
+  // ---- C. one thread per pixel: slot list, then front-to-back compositing ----
+  int cnt = 0;
+  for (int blk = 0; blk < nblk && cnt < K; ++blk) {
+    unsigned w = sm.u.r.bits[tid][blk];
+    while (w && cnt < K) {
+      const int bpos = __ffs(w) - 1;
+      w &= w - 1;
+      sm.u.r.lists[tid][cnt++] = (unsigned short)(blk * 32 + bpos);
+    }
+  }
+  const int nh = cnt;  // <= K
+  {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, T = 1.0f, wsum = 0.0f;
+    const bool ac = q.accumulation == PS_ACCUM_ALPHACOMPOSITE;
+    for (int k = 0; k < nh; ++k) {
+      const int ci = sm.u.r.lists[tid][k];
+      const Cand cd = sm.cand[ci];
+      const float4 f = sm.feat[ci];
+      const float a = alpha_of(dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf)), q);
+      float wgt = a;
+      if (ac) {
+        wgt = T * a;
+        T *= 1.0f - a;
       } else {
-        wgt = a;
         wsum += a;
       }
-      if (cached) {
-        if (valid) {
-#pragma unroll
-          for (int c = 0; c < MAXC_SMEM; ++c)
-            if (c < C) acc[c] += wgt * sm.f[c][ci];
+      acc0 += wgt * f.x;
+      acc1 += wgt * f.y;
+      acc2 += wgt * f.z;
+      acc3 += wgt * f.w;
+    }
+    if (inimg) {
+      const float norm = (q.accumulation == PS_ACCUM_WSUMNORM) ? fmaxf(wsum, 1e-4f) : 1.0f;
+      const bool dv = q.accumulation == PS_ACCUM_WSUMNORM;
+      float* o = q.out + ((size_t)b * C * S + yi) * S + xi;
+      const size_t cs = (size_t)S * S;
+      o[0] = dv ? acc0 / norm : acc0;
+      if (C > 1) o[cs] = dv ? acc1 / norm : acc1;
+      if (C > 2) o[2 * cs] = dv ? acc2 / norm : acc2;
+      if (C > 3) o[3 * cs] = dv ? acc3 / norm : acc3;
+      q.empty[((size_t)b * S + yi) * S + xi] = (nh == 0);
+      // feature widths beyond 4 (non-RGB feature splats): channels re-gathered from global memory
+      for (int c0 = 4; c0 < C; ++c0) {
+        const float* fc = featb + (size_t)c0 * P;
+        float acc = 0.f, Tc = 1.0f;
+        for (int k = 0; k < nh; ++k) {
+          const Cand cd = sm.cand[sm.u.r.lists[tid][k]];
+          const float a = alpha_of(dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf)), q);
+          float wgt = a;
+          if (ac) {
+            wgt = Tc * a;
+            Tc *= 1.0f - a;
+          }
+          acc += wgt * __ldg(fc + cd.id);
         }
-      } else if (k < K) {
-        st.w[k] = valid ? wgt : 0.0f;
+        o[c0 * cs] = dv ? acc / norm : acc;
       }
     }
-    __syncwarp();
-    const size_t pixoff = ((size_t)b * S + pyi) * S + pxi;
-    store_rows(q, st, pixoff, lane);
-    if (q.accumulation != PS_ACCUM_ALPHACOMPOSITE) {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(FULL, wsum, off);
-    }
-    const float norm = (q.accumulation == PS_ACCUM_WSUMNORM) ? fmaxf(wsum, 1e-4f) : 1.0f;
-    if (cached) {
-#pragma unroll
-      for (int c = 0; c < MAXC_SMEM; ++c) {
-        if (c < C) {
-          float v = acc[c];
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-          if (lane == 0) sm.col[c][pix] = (q.accumulation == PS_ACCUM_WSUMNORM) ? v / norm : v;
-        }
-      }
-    } else {
-      const int nhk = min(nh, K);
-      for (int c = lane; c < C; c += 32) {
-        const float* fc = q.feat + ((size_t)b * C + c) * P - base;  // st.idx holds packed ids
-        float v = 0.0f;
-        for (int k = 0; k < nhk; ++k) v += st.w[k] * fc[st.idx[k]];
-        if (q.accumulation == PS_ACCUM_WSUMNORM) v = v / norm;
-        q.out[(((size_t)b * C + c) * S + pyi) * S + pxi] = v;
-      }
-    }
-    __syncwarp();
   }
-  if (cached) {
-    __syncthreads();
-    if (inimg)
-      for (int c = 0; c < C; ++c) q.out[(((size_t)b * C + c) * S + yi) * S + xi] = sm.col[c][tid];
+  __syncwarp();  // a pixel's list is read below by the other lanes of the warp that wrote it
+
+  // ---- D. maps: lane l owns output slots 4l..4l+3 of the current pixel ----
+  if (q.idx || q.zbuf || q.dist2) {
+    const int32_t base = (int32_t)((size_t)b * P);
+    for (int j = 0; j < 32; ++j) {
+      if (!__shfl_sync(FULL, (int)inimg, j)) continue;
+      const int pix = warp * 32 + j;
+      const int nhj = __shfl_sync(FULL, nh, j);
+      const float xfj = __shfl_sync(FULL, xf, j), yfj = __shfl_sync(FULL, yf, j);
+      const int pxi = tx * TILE + (pix & 7), pyi = ty * TILE + (pix >> 3);
+      int id4[4] = {-1, -1, -1, -1};
+      float z4[4] = {-1.f, -1.f, -1.f, -1.f}, d4[4] = {-1.f, -1.f, -1.f, -1.f};
+      const int k0 = 4 * lane;
+      if (k0 < nhj) {
+        const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pix][k0]);
+        const unsigned short ls[4] = {(unsigned short)(L.x & 0xffffu), (unsigned short)(L.x >> 16),
+                                      (unsigned short)(L.y & 0xffffu), (unsigned short)(L.y >> 16)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k0 + e < nhj) {
+            const Cand cd = sm.cand[ls[e]];
+            id4[e] = base + cd.id;
+            z4[e] = cd.z;
+            d4[e] = dist2_rn(__fsub_rn(cd.x, xfj), __fsub_rn(cd.y, yfj));
+          }
+      }
+      store_slots(q, ((size_t)b * S + pyi) * S + pxi, lane, id4, z4, d4);
+    }
   }
 }
 
-// Overflow path: tiles with more than CAP candidates.  Streams the candidate list in chunks of CAPB,
-// sorts each chunk, and merges the chunk's hits (already ordered) into each pixel's running top-K.
+// Overflow path: tiles with more than CAP candidates.  Streams the candidates in chunks of CAPB (from the
+// tile's list, or by rescanning the whole cloud when even the list overflowed), sorts each chunk, and merges
+// the chunk's hits (already ordered) into each pixel's running top-K.  Slow, exact, never drops a point.
 struct BigSmem {
   unsigned long long key[CAPB];
   float2 xy[CAPB];
-  unsigned long long topA[MAXK][FINE_THREADS];
-  unsigned long long topB[MAXK][FINE_THREADS];
-  RowStage stage[FINE_THREADS / 32];
+  unsigned long long topA[MAXK][TPB];
+  unsigned long long topB[MAXK][TPB];
+  int id4[TPB / 32][MAXK];
+  float z4[TPB / 32][MAXK];
+  float d4[TPB / 32][MAXK];
+  float w4[TPB / 32][MAXK];
 };
 
-__global__ void __launch_bounds__(FINE_THREADS) fine_big_kernel(FineParams q) {
+__global__ void __launch_bounds__(TPB) fine_big_kernel(FineParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BigSmem& sm = *reinterpret_cast<BigSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -524,56 +694,66 @@ __global__ void __launch_bounds__(FINE_THREADS) fine_big_kernel(FineParams q) {
     const int b = bt / nt2, t = bt - b * nt2;
     const int ty = t / q.nt, tx = t - ty * q.nt;
     const int n = q.tile_count[bt];
+    const bool rescan = n > CAPG;  // the list is incomplete: derive the candidates from the whole cloud
+    const int total = rescan ? P : n;
     const int xi = tx * TILE + (tid & 7), yi = ty * TILE + (tid >> 3);
     const bool inimg = xi < S && yi < S;
     const float xf = pix_to_ndc(S - 1 - xi, S), yf = pix_to_ndc(S - 1 - yi, S);
-    const float* ptsb = q.pts + (size_t)b * P * 3;
-    const int* lst = q.list + (size_t)b * q.cap_per_view + q.tile_start[bt];
-    unsigned long long(*A)[FINE_THREADS] = sm.topA;
-    unsigned long long(*Bv)[FINE_THREADS] = sm.topB;
+    const float4* p4 = q.pts4 + (size_t)b * P;
+    const int* lst = q.list + (size_t)bt * CAPG;
+    unsigned long long(*A)[TPB] = sm.topA;
+    unsigned long long(*Bv)[TPB] = sm.topB;
     int cntA = 0;
-    for (int c0 = 0; c0 < n; c0 += CAPB) {
-      const int m = min(CAPB, n - c0);
+    for (int c0 = 0; c0 < total; c0 += CAPB) {
+      const int m = min(CAPB, total - c0);
       int N = 2;
       while (N < m) N <<= 1;
       __syncthreads();
-      for (int i = tid; i < N; i += FINE_THREADS) {
+      for (int i = tid; i < N; i += TPB) {
         unsigned long long key = ~0ull;
         if (i < m) {
-          const int p = lst[c0 + i];
-          const float z = ptsb[(size_t)p * 3 + 2] + 0.0f;
-          key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned)p;
+          const int p = rescan ? (c0 + i) : lst[c0 + i];
+          const float4 v = p4[p];
+          bool take = true;
+          if (rescan) {
+            int a0, a1, b0, b1;
+            take = tile_range(v.x, v.y, v.z, q.g, a0, a1, b0, b1) && tx >= a0 && tx <= a1 && ty >= b0 && ty <= b1;
+          }
+          if (take) key = ((unsigned long long)__float_as_uint(v.z + 0.0f) << 32) | (unsigned)p;
         }
         sm.key[i] = key;
       }
       __syncthreads();
-      bitonic_sort_u64(sm.key, N, tid, FINE_THREADS);
-      for (int i = tid; i < m; i += FINE_THREADS) {
-        const int p = (int)(unsigned)(sm.key[i] & 0xffffffffull);
-        sm.xy[i] = make_float2(-ptsb[(size_t)p * 3], -ptsb[(size_t)p * 3 + 1]);
+      bitonic_sort_u64(sm.key, N, tid, TPB);
+      for (int i = tid; i < m; i += TPB) {
+        const unsigned long long key = sm.key[i];
+        if (key != ~0ull) {
+          const float4 v = p4[(int)(unsigned)(key & 0xffffffffull)];
+          sm.xy[i] = make_float2(-v.x, -v.y);
+        }
       }
       __syncthreads();
       // merge: A (sorted, cntA) with this chunk's hits (sorted) -> Bv, keeping the K smallest
       int ia = 0, nb = 0;
       for (int i = 0; i < m; ++i) {
+        const unsigned long long key = sm.key[i];
+        if (key == ~0ull) break;  // rejected entries sort to the end
         const float2 c = sm.xy[i];
-        const float d2 = dist2_rn(c.x - xf, c.y - yf);
+        const float d2 = dist2_rn(__fsub_rn(c.x, xf), __fsub_rn(c.y, yf));
         if (d2 < q.r2 && nb < K) {
-          const unsigned long long key = sm.key[i];
           while (ia < cntA && nb < K && A[ia][tid] < key) Bv[nb++][tid] = A[ia++][tid];
           if (nb < K) Bv[nb++][tid] = key;
         }
       }
       while (ia < cntA && nb < K) Bv[nb++][tid] = A[ia++][tid];
       cntA = nb;
-      unsigned long long(*tmp)[FINE_THREADS] = A;
+      unsigned long long(*tmp)[TPB] = A;
       A = Bv;
       Bv = tmp;
     }
     if (inimg) q.empty[((size_t)b * S + yi) * S + xi] = (cntA == 0);
     __syncwarp();
-    // phase 2 from keys; coordinates and features are gathered from global memory
-    RowStage& st = sm.stage[warp];
+    // one lane per output slot; coordinates and features are gathered from global memory
     const int rounds = (K + 31) >> 5;
     const int32_t base = (int32_t)((size_t)b * P);
     for (int j = 0; j < 32; ++j) {
@@ -581,7 +761,7 @@ __global__ void __launch_bounds__(FINE_THREADS) fine_big_kernel(FineParams q) {
       const int pix = warp * 32 + j;
       const int nh = __shfl_sync(FULL, cntA, j);
       const float xfj = __shfl_sync(FULL, xf, j), yfj = __shfl_sync(FULL, yf, j);
-      const int pxi = __shfl_sync(FULL, xi, j), pyi = __shfl_sync(FULL, yi, j);
+      const int pxi = tx * TILE + (pix & 7), pyi = ty * TILE + (pix >> 3);
       float tcarry = 1.0f, wsum = 0.0f;
       for (int r = 0; r < rounds; ++r) {
         const int k = r * 32 + lane;
@@ -590,11 +770,11 @@ __global__ void __launch_bounds__(FINE_THREADS) fine_big_kernel(FineParams q) {
         int pid = -1;
         if (valid) {
           const int p = (int)(unsigned)(A[k][pix] & 0xffffffffull);
-          const float* pt = ptsb + (size_t)p * 3;
-          d2 = dist2_rn(-pt[0] - xfj, -pt[1] - yfj);
-          z = pt[2];
+          const float4 v = p4[p];
+          d2 = dist2_rn(__fsub_rn(-v.x, xfj), __fsub_rn(-v.y, yfj));
+          z = v.z;
           pid = base + p;
-          a = alpha_of(d2, q.denom, q.tau);
+          a = alpha_of(d2, q);
         }
         float wgt = 0.0f;
         if (r * 32 < nh) {
@@ -615,15 +795,19 @@ __global__ void __launch_bounds__(FINE_THREADS) fine_big_kernel(FineParams q) {
           }
         }
         if (k < K) {
-          st.idx[k] = pid;
-          st.z[k] = z;
-          st.d2[k] = d2;
-          st.w[k] = valid ? wgt : 0.0f;
+          sm.id4[warp][k] = pid;
+          sm.z4[warp][k] = z;
+          sm.d4[warp][k] = d2;
+          sm.w4[warp][k] = valid ? wgt : 0.0f;
         }
       }
       __syncwarp();
       const size_t pixoff = ((size_t)b * S + pyi) * S + pxi;
-      store_rows(q, st, pixoff, lane);
+      for (int k = lane; k < K; k += 32) {
+        if (q.idx) q.idx[pixoff * K + k] = sm.id4[warp][k];
+        if (q.zbuf) q.zbuf[pixoff * K + k] = sm.z4[warp][k];
+        if (q.dist2) q.dist2[pixoff * K + k] = sm.d4[warp][k];
+      }
       if (q.accumulation != PS_ACCUM_ALPHACOMPOSITE) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(FULL, wsum, off);
@@ -633,7 +817,7 @@ __global__ void __launch_bounds__(FINE_THREADS) fine_big_kernel(FineParams q) {
       for (int c = lane; c < C; c += 32) {
         const float* fc = q.feat + ((size_t)b * C + c) * P - base;
         float v = 0.0f;
-        for (int k = 0; k < nhk; ++k) v += st.w[k] * fc[st.idx[k]];
+        for (int k = 0; k < nhk; ++k) v += sm.w4[warp][k] * fc[sm.id4[warp][k]];
         if (q.accumulation == PS_ACCUM_WSUMNORM) v = v / norm;
         q.out[(((size_t)b * C + c) * S + pyi) * S + pxi] = v;
       }
@@ -681,22 +865,16 @@ __global__ void __launch_bounds__(BG_TILE* BG_TILE) bgmask_kernel(const uint8_t*
 // ------------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------------
-static int tile_span(double radius_px) { return (int)((2.0 * (radius_px + 1.0) + 1.0) / TILE) + 2; }
-
 struct SplatLayout {
   int nt, nt2;
-  long long cap_per_view;
   size_t bytes;
-  size_t off_count, off_start, off_list, off_empty, off_ovf;
+  size_t off_count, off_ovf, off_list, off_empty, off_pts4;
 };
 
-static SplatLayout splat_layout(int B, int P, int S, double radius_px) {
+static SplatLayout splat_layout(int B, int P, int S) {
   SplatLayout L;
   L.nt = (S + TILE - 1) / TILE;
   L.nt2 = L.nt * L.nt;
-  const long long span = tile_span(radius_px);
-  L.cap_per_view = (long long)P * span * span;
-  if (L.cap_per_view > (long long)P * L.nt2) L.cap_per_view = (long long)P * L.nt2;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     off = align_up(off, 256);
@@ -706,19 +884,21 @@ static SplatLayout splat_layout(int B, int P, int S, double radius_px) {
   };
   L.off_count = take(sizeof(int) * (size_t)B * L.nt2);
   L.off_ovf = take(sizeof(int) * (1 + (size_t)B * L.nt2));  // adjacent to counts: one memset clears both
-  L.off_start = take(sizeof(int) * (size_t)B * L.nt2);
-  L.off_list = take(sizeof(int) * (size_t)B * (size_t)L.cap_per_view);
+  L.off_list = take(sizeof(int) * (size_t)B * L.nt2 * CAPG);
   L.off_empty = take((size_t)B * S * S);
+  L.off_pts4 = take(sizeof(float4) * (size_t)B * P);
   L.bytes = align_up(off, 256);
   return L;
 }
 
-static int splat_points_impl(const float* pts, const float* feat, int B, int P, int C, int S, int K, double radius_px,
-                             double tau, int rad_pow, int accumulation, int bg_ksize, float* out, uint8_t* bg_mask,
-                             int32_t* idx, float* zbuf, float* dist2, void* workspace, size_t workspace_bytes,
-                             cudaStream_t stream) {
-  PS_CHECK_ARG(pts && feat && out && bg_mask && workspace);
-  PS_CHECK_ARG(B >= 0 && P >= 0 && C >= 1 && S >= 1);
+// depth != null: project from depth (forward_justpts); else pts (B,P,3) is the cloud.
+static int splat_impl(const float* depth, const float* mats, int W, float eps, const float* pts, const float* feat,
+                      int B, int P, int C, int S, int K, double radius_px, double tau, int rad_pow, int accumulation,
+                      int bg_ksize, float* out, uint8_t* bg_mask, int32_t* idx, float* zbuf, float* dist2,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PS_CHECK_ARG((depth && mats) || pts);
+  PS_CHECK_ARG((feat || P == 0) && out && bg_mask && workspace);
+  PS_CHECK_ARG(B >= 0 && P >= 0 && C >= 1 && S >= 1 && S <= 8192);
   PS_CHECK_ARG(K >= 1);
   if (K > MAXK) return fail(PS_EUNSUPPORTED, "%s: points_per_pixel exceeds PS_MAX_POINTS_PER_PIXEL%s", __func__);
   PS_CHECK_ARG(accumulation >= 0 && accumulation <= 2);
@@ -726,14 +906,14 @@ static int splat_points_impl(const float* pts, const float* feat, int B, int P, 
   PS_CHECK_ARG(radius_px > 0.0 && radius_px <= 64.0);
   PS_CHECK_ARG((size_t)B * P < 0x7fffffffull);  // packed indices are int32, as in PyTorch3D
   if (B == 0) return PS_OK;
-  const SplatLayout L = splat_layout(B, P, S, radius_px);
+  const SplatLayout L = splat_layout(B, P, S);
   if (workspace_bytes < L.bytes) return fail(PS_EWORKSPACE, "%s: workspace too small%s", __func__);
   char* ws = (char*)workspace;
   int* tile_count = (int*)(ws + L.off_count);
   int* ovf = (int*)(ws + L.off_ovf);
-  int* tile_start = (int*)(ws + L.off_start);
   int* list = (int*)(ws + L.off_list);
   uint8_t* empty = (uint8_t*)(ws + L.off_empty);
+  float4* pts4 = (float4*)(ws + L.off_pts4);
 
   const double radius = radius_px / (double)S * 2.0;  // z_buffer_layers.py:77
   const float rf = (float)radius;
@@ -741,26 +921,24 @@ static int splat_points_impl(const float* pts, const float* feat, int B, int P, 
   g.S = S;
   g.nt = L.nt;
   g.half_S = 0.5f * (float)S;
-  g.rp = (float)(radius_px + 1.0);
+  g.rp = (float)(radius_px + 1.0 / 64.0);
   g.lim = 1.0f + rf + 4.0f / (float)S;
 
   PS_CUDA(cudaMemsetAsync(tile_count, 0, (L.off_ovf - L.off_count) + sizeof(int), stream));
   if (P > 0) {
     dim3 grid((P + 255) / 256, B);
-    bin_count_kernel<<<grid, 256, 0, stream>>>(pts, P, g, tile_count);
-    PS_LAUNCHED();
-    bin_scan_kernel<<<B, 1024, 0, stream>>>(tile_count, tile_start, L.nt2);
-    PS_LAUNCHED();
-    bin_fill_kernel<<<grid, 256, 0, stream>>>(pts, P, g, tile_count, tile_start, list, L.cap_per_view);
+    ProjectArgs pa{depth, mats, W, eps};
+    if (depth)
+      bin_kernel<true><<<grid, 256, 0, stream>>>(pa, nullptr, P, g, pts4, tile_count, list);
+    else
+      bin_kernel<false><<<grid, 256, 0, stream>>>(pa, pts, P, g, pts4, tile_count, list);
     PS_LAUNCHED();
   }
   FineParams q;
-  q.pts = pts;
+  q.pts4 = pts4;
   q.feat = feat;
   q.tile_count = tile_count;
-  q.tile_start = tile_start;
   q.list = list;
-  q.cap_per_view = L.cap_per_view;
   q.P = P;
   q.C = C;
   q.S = S;
@@ -768,8 +946,13 @@ static int splat_points_impl(const float* pts, const float* feat, int B, int P, 
   q.nt = L.nt;
   q.r2 = rf * rf;
   q.denom = (float)pow(radius, (double)rad_pow);
+  {
+    int e = 0;
+    q.inv_denom = (frexpf(q.denom, &e) == 0.5f) ? 1.0f / q.denom : 0.0f;  // exact reciprocal only
+  }
   q.tau = (float)tau;
   q.accumulation = accumulation;
+  q.g = g;
   q.out = out;
   q.empty = empty;
   q.idx = idx;
@@ -782,17 +965,17 @@ static int splat_points_impl(const float* pts, const float* feat, int B, int P, 
   int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
   if (smem_set_for_device != dev) {
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem<CAP>)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
     PS_CUDA(cudaFuncSetAttribute(fine_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
     smem_set_for_device = dev;
   }
   {
     dim3 grid(L.nt2, B);
     PS_TIME_BEGIN("fine_kernel", stream);
-    fine_kernel<<<grid, FINE_THREADS, sizeof(FineSmem<CAP>), stream>>>(q);
+    fine_kernel<<<grid, TPB, sizeof(FineSmem), stream>>>(q);
     PS_TIME_END(stream);
     PS_LAUNCHED();
-    fine_big_kernel<<<296, FINE_THREADS, sizeof(BigSmem), stream>>>(q);
+    fine_big_kernel<<<296, TPB, sizeof(BigSmem), stream>>>(q);
     PS_LAUNCHED();
   }
   {
@@ -833,39 +1016,34 @@ int ps_project_cloud(const float* cloud, const float* mats3, int B, int P, float
 }
 
 size_t ps_splat_workspace_bytes(int B, int P, int S, double radius_px) {
-  if (B <= 0 || P < 0 || S < 1 || !(radius_px > 0.0)) return 256;
-  return splat_layout(B, P, S, radius_px).bytes;
+  (void)radius_px;
+  if (B <= 0 || P < 0 || S < 1) return 256;
+  return splat_layout(B, P, S).bytes;
 }
 
 int ps_splat_points(const float* pts, const float* feat, int B, int P, int C, int S, int K, double radius_px,
                     double tau, int rad_pow, int accumulation, int bg_ksize, float* out, uint8_t* bg_mask,
                     int32_t* idx, float* zbuf, float* dist2, void* workspace, size_t workspace_bytes, void* stream) {
-  return splat_points_impl(pts, feat, B, P, C, S, K, radius_px, tau, rad_pow, accumulation, bg_ksize, out, bg_mask, idx,
-                           zbuf, dist2, workspace, workspace_bytes, (cudaStream_t)stream);
+  PS_CHECK_ARG(pts || P == 0 || B == 0);
+  static const float dummy = 0.f;
+  return splat_impl(nullptr, nullptr, 0, 0.f, pts ? pts : &dummy, feat, B, P, C, S, K, radius_px, tau, rad_pow,
+                    accumulation, bg_ksize, out, bg_mask, idx, zbuf, dist2, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }
 
 size_t ps_splat_fwd_workspace_bytes(int B, int W, int S, double radius_px) {
   if (B <= 0 || W < 2) return 256;
-  const size_t P = (size_t)W * W;
-  return align_up(sizeof(float) * 3 * P * B, 256) + ps_splat_workspace_bytes(B, (int)P, S, radius_px);
+  return ps_splat_workspace_bytes(B, W * W, S, radius_px);
 }
 
 int ps_splat_fwd(const float* depth, const float* feat, const float* mats, int B, int W, int C, int S, int K,
                  double radius_px, double tau, int rad_pow, int accumulation, int bg_ksize, float eps, float* out,
                  uint8_t* bg_mask, int32_t* idx, float* zbuf, float* dist2, void* workspace, size_t workspace_bytes,
                  void* stream) {
-  PS_CHECK_ARG(workspace);
+  PS_CHECK_ARG(depth && mats);
   PS_CHECK_ARG(B >= 0 && W >= 2 && W <= 4096);
-  if (B == 0) return PS_OK;
-  const size_t P = (size_t)W * W;
-  const size_t pts_bytes = align_up(sizeof(float) * 3 * P * B, 256);
-  if (workspace_bytes < pts_bytes) return fail(PS_EWORKSPACE, "%s: workspace too small%s", __func__);
-  float* pts = (float*)workspace;
-  int rc = ps_project_pts(depth, mats, B, W, eps, pts, nullptr, stream);
-  if (rc != PS_OK) return rc;
-  return splat_points_impl(pts, feat, B, (int)P, C, S, K, radius_px, tau, rad_pow, accumulation, bg_ksize, out, bg_mask,
-                           idx, zbuf, dist2, (char*)workspace + pts_bytes, workspace_bytes - pts_bytes,
-                           (cudaStream_t)stream);
+  return splat_impl(depth, mats, W, eps, nullptr, feat, B, W * W, C, S, K, radius_px, tau, rad_pow, accumulation,
+                    bg_ksize, out, bg_mask, idx, zbuf, dist2, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

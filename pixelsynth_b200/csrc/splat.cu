@@ -8,10 +8,10 @@
 // Design (HBM-bound: 69.0 MB of mandatory output per 256x256 view when the idx/z maps are emitted):
 //   1. bin_kernel (projection fused in): every point is appended, with warp-aggregated atomics, to the
 //      fixed-capacity candidate list of each 8x8-pixel tile its disc can reach (tight, conservative box).
-//   2. fine_kernel, one 64-thread CTA per tile: candidates are sorted ONCE per tile by the canonical key
+//   2. fine_kernel, one 128-thread CTA per tile: candidates are sorted ONCE per tile by the canonical key
 //      (z, point id) with a shared-memory counting sort; warps then ballot the exact membership test of 32
 //      sorted candidates against the tile's 64 pixels, so every pixel's hits come out already in output
-//      order as bit masks; one thread per pixel expands its masks and composites front to back; finally
+//      order as bit masks; two threads per pixel expand the masks and composite front to back; finally
 //      each warp streams a pixel's K slots of idx / zbuf / dist2 with 16-byte coalesced stores.
 //   3. tiles with more candidates than the shared-memory capacity are queued for fine_big_kernel, which
 //      streams the list (or, if even the list overflowed, the whole cloud) in sorted chunks and merges into a
@@ -25,7 +25,9 @@
 namespace ps {
 
 constexpr int TILE = 8;
-constexpr int TPB = TILE * TILE;  // threads per tile CTA
+constexpr int NPIX = TILE * TILE;  // pixels per tile
+constexpr int FTPB = 128;          // threads of the tile kernel: two per pixel
+constexpr int TPB = NPIX;          // threads of the overflow kernel: one per pixel
 constexpr int CAP = 512;          // candidates per tile handled by the shared-memory fast path
 constexpr int CAPG = 1024;        // capacity of a tile's candidate list in global memory
 constexpr int CAPB = 1024;        // chunk size of the overflow path
@@ -301,6 +303,14 @@ __device__ __forceinline__ float alpha_of(float d2, const FineParams& q) {
   return a;
 }
 
+// tau == 1 and an exact reciprocal of r^rad_pow
+__device__ __forceinline__ float alpha_fast(float d2, float inv_denom) {
+  const float d = fminf(fmaxf(d2 * inv_denom, 1e-3f), 1.0f);
+  float s;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d));
+  return 1.0f - s;
+}
+
 __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* __restrict__ key, int N, int tid, int nthreads) {
   for (int k = 2; k <= N; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -325,12 +335,12 @@ struct __align__(16) Cand {
 };
 
 struct SortScratch {
-  unsigned hist[NB + 2];        // bucket counts -> exclusive starts; hist[NB] = n
+  unsigned hist[NB + 4];        // bucket counts -> exclusive starts; hist[NB] = n
   unsigned long long key[CAP];  // (z bits << 32) | point id, in bucket order
 };
 struct RasterScratch {
-  unsigned bits[TPB][BSTRIDE];         // per pixel: hit mask over the sorted candidates, 32 per word
-  unsigned short lists[TPB][LSTRIDE];  // per pixel: candidate index of output slot k
+  unsigned bits[NPIX][BSTRIDE];         // per pixel: hit mask over the sorted candidates, 32 per word
+  unsigned short lists[NPIX][LSTRIDE];  // per pixel: candidate index of output slot k
 };
 struct FineSmem {
   Cand cand[CAP];
@@ -339,8 +349,9 @@ struct FineSmem {
     SortScratch s;
     RasterScratch r;
   } u;
+  float ndcx[TILE], ndcy[TILE];  // NDC centres of the tile's pixel columns / rows
   unsigned zmin, zmax, maxcount;
-  unsigned warp_tot[TPB / 32];
+  unsigned warp_tot[FTPB / 32];
 };
 
 // writes the K output slots 4*lane .. 4*lane+3 of one pixel (called by a full warp)
@@ -365,17 +376,31 @@ __device__ __forceinline__ void store_slots(const FineParams& q, size_t pixoff, 
   }
 }
 
-// One 64-thread CTA per 8x8-pixel tile.
+__device__ __forceinline__ float4 gather_feat(const float* __restrict__ featb, int C, int P, int pid) {
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+  f.x = __ldg(featb + pid);
+  if (C > 1) f.y = __ldg(featb + (size_t)P + pid);
+  if (C > 2) f.z = __ldg(featb + 2 * (size_t)P + pid);
+  if (C > 3) f.w = __ldg(featb + 3 * (size_t)P + pid);
+  return f;
+}
+
+// One 128-thread CTA per 8x8-pixel tile.
 //   A. load the tile's candidates; counting sort by (z, point id): 1024 buckets over the tile's z range,
 //      exact rank inside the (small) buckets; a bitonic sort is the fallback for degenerate z distributions.
 //   B. each warp takes 32 sorted candidates at a time and ballots the exact membership test against the 64
 //      pixels: pixel p gets, per candidate block, a 32-bit hit word whose set bits are already in output order.
-//   C. one thread per pixel expands its hit words into the slot list and composites front to back.
+//   C. two adjacent lanes per pixel: each expands half of the pixel's hit words into the slot list, then
+//      composites half of the slots front to back; the halves combine as acc0 + T0 * acc1.
 //   D. one warp per pixel row of K slots: gather (id, z), recompute dist2, 16-byte streaming stores.
-__global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
+// FAST: alpha compositing with tau == 1, an exact reciprocal of r^rad_pow and at most 4 feature channels
+// (the reference's shipped configuration); otherwise the same code with the general formulas.
+template <bool FAST>
+__global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FineSmem& sm = *reinterpret_cast<FineSmem*>(smem_raw);
-  constexpr int PER = CAP / TPB;
+  constexpr int PER = CAP / FTPB;
+  constexpr int NWARP = FTPB / 32;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -388,13 +413,12 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
     return;
   }
   const int S = q.S, K = q.K, P = q.P, C = q.C;
-  const int xi = tx * TILE + (tid & 7), yi = ty * TILE + (tid >> 3);
-  const bool inimg = xi < S && yi < S;
-  const float xf = pix_to_ndc(S - 1 - xi, S), yf = pix_to_ndc(S - 1 - yi, S);
 
   // ---- A. load + sort ----
-  for (int i = tid; i < NB + 2; i += TPB) sm.u.s.hist[i] = 0;
-  if (tid == 0) {
+  for (int i = tid; i < (NB + 4) / 4; i += FTPB) reinterpret_cast<uint4*>(sm.u.s.hist)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < TILE) sm.ndcx[tid] = pix_to_ndc(S - 1 - (tx * TILE + tid), S);
+  if (tid >= 32 && tid < 32 + TILE) sm.ndcy[tid - 32] = pix_to_ndc(S - 1 - (ty * TILE + tid - 32), S);
+  if (tid == 64) {
     sm.zmin = 0xffffffffu;
     sm.zmax = 0u;
     sm.maxcount = 0u;
@@ -406,13 +430,13 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
   unsigned zb[PER];
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
-    const int i = tid + j * TPB;
+    const int i = tid + j * FTPB;
     id[j] = (i < n) ? __ldg(lst + i) : 0;
   }
   unsigned lmin = 0xffffffffu, lmax = 0u;
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
-    const int i = tid + j * TPB;
+    const int i = tid + j * FTPB;
     if (i < n) {
       const float4 v = __ldg(p4 + id[j]);
       cx[j] = v.x;
@@ -437,15 +461,15 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
   unsigned bo[PER];
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
-    const int i = tid + j * TPB;
+    const int i = tid + j * FTPB;
     if (i < n) {
       const unsigned bk = (zb[j] - zmin) >> sh;
       bo[j] = (bk << 16) | atomicAdd(&sm.u.s.hist[bk], 1u);
     }
   }
   __syncthreads();
-  {  // exclusive scan of the NB bucket counts; each thread owns NB/TPB consecutive buckets
-    constexpr int BPT = NB / TPB;
+  {  // exclusive scan of the NB bucket counts; each thread owns NB/FTPB consecutive buckets
+    constexpr int BPT = NB / FTPB;
     unsigned v[BPT];
     unsigned tot = 0, mx = 0;
 #pragma unroll
@@ -474,7 +498,9 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
     if (lane == 0) atomicMax(&sm.maxcount, mx);
     __syncthreads();
     unsigned base = incl - tot;
-    for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+#pragma unroll
+    for (int w = 0; w < NWARP - 1; ++w)
+      if (w < warp) base += sm.warp_tot[w];
 #pragma unroll
     for (int e = 0; e < BPT; e += 4)
       *reinterpret_cast<uint4*>(&sm.u.s.hist[tid * BPT + e]) =
@@ -484,7 +510,7 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
-    const int i = tid + j * TPB;
+    const int i = tid + j * FTPB;
     if (i < n)
       sm.u.s.key[sm.u.s.hist[bo[j] >> 16] + (bo[j] & 0xffffu)] =
           ((unsigned long long)zb[j] << 32) | (unsigned)id[j];
@@ -494,7 +520,7 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
   if (sm.maxcount <= (unsigned)MAXBK) {
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      const int i = tid + j * TPB;
+      const int i = tid + j * FTPB;
       if (i < n) {
         const unsigned bk = bo[j] >> 16;
         const unsigned s0 = sm.u.s.hist[bk], c = sm.u.s.hist[bk + 1] - s0;
@@ -510,21 +536,16 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
         cd.z = cz[j];
         cd.id = id[j];
         sm.cand[fin] = cd;
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-        f.x = __ldg(featb + id[j]);
-        if (C > 1) f.y = __ldg(featb + (size_t)P + id[j]);
-        if (C > 2) f.z = __ldg(featb + 2 * (size_t)P + id[j]);
-        if (C > 3) f.w = __ldg(featb + 3 * (size_t)P + id[j]);
-        sm.feat[fin] = f;
+        sm.feat[fin] = gather_feat(featb, C, P, id[j]);
       }
     }
   } else {  // degenerate z distribution (e.g. constant depth): full sort of the 64-bit keys
     int N = 2;
     while (N < n) N <<= 1;
-    for (int i = n + tid; i < N; i += TPB) sm.u.s.key[i] = ~0ull;
+    for (int i = n + tid; i < N; i += FTPB) sm.u.s.key[i] = ~0ull;
     __syncthreads();
-    bitonic_sort_u64(sm.u.s.key, N, tid, TPB);
-    for (int i = tid; i < n; i += TPB) {
+    bitonic_sort_u64(sm.u.s.key, N, tid, FTPB);
+    for (int i = tid; i < n; i += FTPB) {
       const int pid = (int)(unsigned)(sm.u.s.key[i] & 0xffffffffull);
       const float4 v = __ldg(p4 + pid);
       Cand cd;
@@ -533,12 +554,7 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
       cd.z = v.z;
       cd.id = pid;
       sm.cand[i] = cd;
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-      f.x = __ldg(featb + pid);
-      if (C > 1) f.y = __ldg(featb + (size_t)P + pid);
-      if (C > 2) f.z = __ldg(featb + 2 * (size_t)P + pid);
-      if (C > 3) f.w = __ldg(featb + 3 * (size_t)P + pid);
-      sm.feat[i] = f;
+      sm.feat[i] = gather_feat(featb, C, P, pid);
     }
   }
   __syncthreads();  // cand/feat complete; sort scratch is dead from here (aliased by bits/lists)
@@ -549,10 +565,10 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
     float xfc[TILE], yfr[TILE];
 #pragma unroll
     for (int c = 0; c < TILE; ++c) {
-      xfc[c] = pix_to_ndc(S - 1 - (tx * TILE + c), S);
-      yfr[c] = pix_to_ndc(S - 1 - (ty * TILE + c), S);
+      xfc[c] = sm.ndcx[c];
+      yfr[c] = sm.ndcy[c];
     }
-    for (int blk = warp; blk < nblk; blk += TPB / 32) {
+    for (int blk = warp; blk < nblk; blk += NWARP) {
       const int ci = blk * 32 + lane;
       float px = 1e30f, py = 1e30f;  // lanes past the end never hit
       if (ci < n) {
@@ -577,25 +593,41 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
   }
   __syncthreads();
 
-  // ---- C. one thread per pixel: slot list, then front-to-back compositing ----
-  int cnt = 0;
-  for (int blk = 0; blk < nblk && cnt < K; ++blk) {
-    unsigned w = sm.u.r.bits[tid][blk];
-    while (w && cnt < K) {
-      const int bpos = __ffs(w) - 1;
-      w &= w - 1;
-      sm.u.r.lists[tid][cnt++] = (unsigned short)(blk * 32 + bpos);
-    }
-  }
-  const int nh = cnt;  // <= K
+  // ---- C. two lanes per pixel: slot list, then front-to-back compositing ----
+  const int pix = tid >> 1, half = tid & 1;
+  const int xi = tx * TILE + (pix & 7), yi = ty * TILE + (pix >> 3);
+  const bool inimg = xi < S && yi < S;
+  const float xf = sm.ndcx[pix & 7], yf = sm.ndcy[pix >> 3];
+  int nh;
   {
+    // lane 0 expands words [0, mid), lane 1 words [mid, nblk) starting at the hit count of the first half
+    const int mid = (nblk + 1) >> 1;
+    int first = 0;
+    for (int blk = 0; blk < mid; ++blk) first += __popc(sm.u.r.bits[pix][blk]);
+    int pos = half ? first : 0;
+    const int b0 = half ? mid : 0, b1 = half ? nblk : mid;
+    for (int blk = b0; blk < b1 && pos < K; ++blk) {
+      unsigned w = sm.u.r.bits[pix][blk];
+      while (w && pos < K) {
+        const int bpos = __ffs(w) - 1;
+        w &= w - 1;
+        sm.u.r.lists[pix][pos++] = (unsigned short)(blk * 32 + bpos);
+      }
+    }
+    nh = min(__shfl_sync(FULL, pos, lane | 1), K);  // lane 1 ends at the pixel's total hit count
+  }
+  __syncwarp();
+  {
+    const int m2 = (nh + 1) >> 1;
+    const int k0 = half ? m2 : 0, k1 = half ? nh : m2;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, T = 1.0f, wsum = 0.0f;
-    const bool ac = q.accumulation == PS_ACCUM_ALPHACOMPOSITE;
-    for (int k = 0; k < nh; ++k) {
-      const int ci = sm.u.r.lists[tid][k];
+    const bool ac = FAST || q.accumulation == PS_ACCUM_ALPHACOMPOSITE;
+    for (int k = k0; k < k1; ++k) {
+      const int ci = sm.u.r.lists[pix][k];
       const Cand cd = sm.cand[ci];
       const float4 f = sm.feat[ci];
-      const float a = alpha_of(dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf)), q);
+      const float d2 = dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf));
+      const float a = FAST ? alpha_fast(d2, q.inv_denom) : alpha_of(d2, q);
       float wgt = a;
       if (ac) {
         wgt = T * a;
@@ -603,14 +635,26 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
       } else {
         wsum += a;
       }
-      acc0 += wgt * f.x;
-      acc1 += wgt * f.y;
-      acc2 += wgt * f.z;
-      acc3 += wgt * f.w;
+      acc0 = fmaf(wgt, f.x, acc0);
+      acc1 = fmaf(wgt, f.y, acc1);
+      acc2 = fmaf(wgt, f.z, acc2);
+      acc3 = fmaf(wgt, f.w, acc3);
     }
-    if (inimg) {
-      const float norm = (q.accumulation == PS_ACCUM_WSUMNORM) ? fmaxf(wsum, 1e-4f) : 1.0f;
-      const bool dv = q.accumulation == PS_ACCUM_WSUMNORM;
+    // combine the halves: second-half terms are attenuated by the first half's transmittance
+    const float T0 = __shfl_sync(FULL, T, lane & ~1);
+    const float sc = (half && ac) ? T0 : 1.0f;
+    acc0 *= sc;
+    acc1 *= sc;
+    acc2 *= sc;
+    acc3 *= sc;
+    acc0 += __shfl_xor_sync(FULL, acc0, 1);
+    acc1 += __shfl_xor_sync(FULL, acc1, 1);
+    acc2 += __shfl_xor_sync(FULL, acc2, 1);
+    acc3 += __shfl_xor_sync(FULL, acc3, 1);
+    wsum += __shfl_xor_sync(FULL, wsum, 1);
+    if (inimg && half == 0) {
+      const bool dv = !FAST && q.accumulation == PS_ACCUM_WSUMNORM;
+      const float norm = dv ? fmaxf(wsum, 1e-4f) : 1.0f;
       float* o = q.out + ((size_t)b * C * S + yi) * S + xi;
       const size_t cs = (size_t)S * S;
       o[0] = dv ? acc0 / norm : acc0;
@@ -618,40 +662,41 @@ __global__ void __launch_bounds__(TPB) fine_kernel(FineParams q) {
       if (C > 2) o[2 * cs] = dv ? acc2 / norm : acc2;
       if (C > 3) o[3 * cs] = dv ? acc3 / norm : acc3;
       q.empty[((size_t)b * S + yi) * S + xi] = (nh == 0);
-      // feature widths beyond 4 (non-RGB feature splats): channels re-gathered from global memory
-      for (int c0 = 4; c0 < C; ++c0) {
-        const float* fc = featb + (size_t)c0 * P;
-        float acc = 0.f, Tc = 1.0f;
-        for (int k = 0; k < nh; ++k) {
-          const Cand cd = sm.cand[sm.u.r.lists[tid][k]];
-          const float a = alpha_of(dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf)), q);
-          float wgt = a;
-          if (ac) {
-            wgt = Tc * a;
-            Tc *= 1.0f - a;
+      if (!FAST) {
+        // feature widths beyond 4 (non-RGB feature splats): channels re-gathered from global memory
+        for (int c0 = 4; c0 < C; ++c0) {
+          const float* fc = featb + (size_t)c0 * P;
+          float acc = 0.f, Tc = 1.0f;
+          for (int k = 0; k < nh; ++k) {
+            const Cand cd = sm.cand[sm.u.r.lists[pix][k]];
+            const float a = alpha_of(dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf)), q);
+            float wgt = a;
+            if (ac) {
+              wgt = Tc * a;
+              Tc *= 1.0f - a;
+            }
+            acc += wgt * __ldg(fc + cd.id);
           }
-          acc += wgt * __ldg(fc + cd.id);
+          o[c0 * cs] = dv ? acc / norm : acc;
         }
-        o[c0 * cs] = dv ? acc / norm : acc;
       }
     }
   }
-  __syncwarp();  // a pixel's list is read below by the other lanes of the warp that wrote it
 
-  // ---- D. maps: lane l owns output slots 4l..4l+3 of the current pixel ----
+  // ---- D. maps: lane l owns output slots 4l..4l+3 of the current pixel; a warp streams its 16 pixels ----
   if (q.idx || q.zbuf || q.dist2) {
     const int32_t base = (int32_t)((size_t)b * P);
-    for (int j = 0; j < 32; ++j) {
-      if (!__shfl_sync(FULL, (int)inimg, j)) continue;
-      const int pix = warp * 32 + j;
-      const int nhj = __shfl_sync(FULL, nh, j);
-      const float xfj = __shfl_sync(FULL, xf, j), yfj = __shfl_sync(FULL, yf, j);
-      const int pxi = tx * TILE + (pix & 7), pyi = ty * TILE + (pix >> 3);
+    for (int j = 0; j < 16; ++j) {
+      if (!__shfl_sync(FULL, (int)inimg, 2 * j)) continue;
+      const int pj = warp * 16 + j;
+      const int nhj = __shfl_sync(FULL, nh, 2 * j);
+      const float xfj = sm.ndcx[pj & 7], yfj = sm.ndcy[pj >> 3];
+      const int pxi = tx * TILE + (pj & 7), pyi = ty * TILE + (pj >> 3);
       int id4[4] = {-1, -1, -1, -1};
       float z4[4] = {-1.f, -1.f, -1.f, -1.f}, d4[4] = {-1.f, -1.f, -1.f, -1.f};
       const int k0 = 4 * lane;
       if (k0 < nhj) {
-        const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pix][k0]);
+        const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pj][k0]);
         const unsigned short ls[4] = {(unsigned short)(L.x & 0xffffu), (unsigned short)(L.x >> 16),
                                       (unsigned short)(L.y & 0xffffu), (unsigned short)(L.y >> 16)};
 #pragma unroll
@@ -965,14 +1010,19 @@ static int splat_impl(const float* depth, const float* mats, int W, float eps, c
   int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
   if (smem_set_for_device != dev) {
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
     PS_CUDA(cudaFuncSetAttribute(fine_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
     smem_set_for_device = dev;
   }
   {
     dim3 grid(L.nt2, B);
     PS_TIME_BEGIN("fine_kernel", stream);
-    fine_kernel<<<grid, TPB, sizeof(FineSmem), stream>>>(q);
+    const bool fast = accumulation == PS_ACCUM_ALPHACOMPOSITE && q.tau == 1.0f && q.inv_denom != 0.0f && C <= 4;
+    if (fast)
+      fine_kernel<true><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+    else
+      fine_kernel<false><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
     PS_TIME_END(stream);
     PS_LAUNCHED();
     fine_big_kernel<<<296, TPB, sizeof(BigSmem), stream>>>(q);

@@ -343,8 +343,9 @@ struct RasterScratch {
   unsigned short lists[NPIX][LSTRIDE];  // per pixel: candidate index of output slot k
 };
 struct FineSmem {
-  Cand cand[CAP];
-  float4 feat[CAP];  // up to 4 feature channels of each candidate
+  Cand cand[CAP + 1];  // [CAP] is the sentinel the padded list entries point at (id -> -1, z = -1)
+  float4 feat[CAP];    // up to 4 feature channels of each candidate
+  float4 pad_;
   union {
     SortScratch s;
     RasterScratch r;
@@ -353,28 +354,6 @@ struct FineSmem {
   unsigned zmin, zmax, maxcount;
   unsigned warp_tot[FTPB / 32];
 };
-
-// writes the K output slots 4*lane .. 4*lane+3 of one pixel (called by a full warp)
-__device__ __forceinline__ void store_slots(const FineParams& q, size_t pixoff, int lane, const int* id4, const float* z4,
-                                            const float* d4) {
-  const int K = q.K;
-  const int k0 = 4 * lane;
-  if (k0 >= K) return;
-  const size_t o = pixoff * K + k0;
-  if ((K & 3) == 0) {
-    if (q.idx) __stcs(reinterpret_cast<int4*>(q.idx + o), make_int4(id4[0], id4[1], id4[2], id4[3]));
-    if (q.zbuf) __stcs(reinterpret_cast<float4*>(q.zbuf + o), make_float4(z4[0], z4[1], z4[2], z4[3]));
-    if (q.dist2) __stcs(reinterpret_cast<float4*>(q.dist2 + o), make_float4(d4[0], d4[1], d4[2], d4[3]));
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (k0 + e < K) {
-        if (q.idx) q.idx[o + e] = id4[e];
-        if (q.zbuf) q.zbuf[o + e] = z4[e];
-        if (q.dist2) q.dist2[o + e] = d4[e];
-      }
-  }
-}
 
 __device__ __forceinline__ float4 gather_feat(const float* __restrict__ featb, int C, int P, int pid) {
   float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -418,6 +397,14 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
   for (int i = tid; i < (NB + 4) / 4; i += FTPB) reinterpret_cast<uint4*>(sm.u.s.hist)[i] = make_uint4(0, 0, 0, 0);
   if (tid < TILE) sm.ndcx[tid] = pix_to_ndc(S - 1 - (tx * TILE + tid), S);
   if (tid >= 32 && tid < 32 + TILE) sm.ndcy[tid - 32] = pix_to_ndc(S - 1 - (ty * TILE + tid - 32), S);
+  if (tid == 65) {
+    Cand sc;
+    sc.x = 0.f;
+    sc.y = 0.f;
+    sc.z = -1.0f;
+    sc.id = -1 - (int32_t)((size_t)b * P);
+    sm.cand[CAP] = sc;
+  }
   if (tid == 64) {
     sm.zmin = 0xffffffffu;
     sm.zmax = 0u;
@@ -615,6 +602,8 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       }
     }
     nh = min(__shfl_sync(FULL, pos, lane | 1), K);  // lane 1 ends at the pixel's total hit count
+    if (half)
+      for (int e = nh; e < ((nh + 3) & ~3); ++e) sm.u.r.lists[pix][e] = (unsigned short)CAP;
   }
   __syncwarp();
   {
@@ -622,8 +611,32 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
     const int k0 = half ? m2 : 0, k1 = half ? nh : m2;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, T = 1.0f, wsum = 0.0f;
     const bool ac = FAST || q.accumulation == PS_ACCUM_ALPHACOMPOSITE;
-    for (int k = k0; k < k1; ++k) {
-      const int ci = sm.u.r.lists[pix][k];
+    const unsigned short* lp = sm.u.r.lists[pix];
+    int k = k0;
+    for (; k + 1 < k1; k += 2) {  // two hits per trip: independent loads and alphas, serial transmittance
+      const int ci0 = lp[k], ci1 = lp[k + 1];
+      const Cand cd0 = sm.cand[ci0], cd1 = sm.cand[ci1];
+      const float4 f0 = sm.feat[ci0], f1 = sm.feat[ci1];
+      const float d20 = dist2_rn(__fsub_rn(cd0.x, xf), __fsub_rn(cd0.y, yf));
+      const float d21 = dist2_rn(__fsub_rn(cd1.x, xf), __fsub_rn(cd1.y, yf));
+      const float a0 = FAST ? alpha_fast(d20, q.inv_denom) : alpha_of(d20, q);
+      const float a1 = FAST ? alpha_fast(d21, q.inv_denom) : alpha_of(d21, q);
+      float w0 = a0, w1 = a1;
+      if (ac) {
+        w0 = T * a0;
+        T *= 1.0f - a0;
+        w1 = T * a1;
+        T *= 1.0f - a1;
+      } else {
+        wsum += a0 + a1;
+      }
+      acc0 = fmaf(w1, f1.x, fmaf(w0, f0.x, acc0));
+      acc1 = fmaf(w1, f1.y, fmaf(w0, f0.y, acc1));
+      acc2 = fmaf(w1, f1.z, fmaf(w0, f0.z, acc2));
+      acc3 = fmaf(w1, f1.w, fmaf(w0, f0.w, acc3));
+    }
+    if (k < k1) {
+      const int ci = lp[k];
       const Cand cd = sm.cand[ci];
       const float4 f = sm.feat[ci];
       const float d2 = dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf));
@@ -683,32 +696,56 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
     }
   }
 
-  // ---- D. maps: lane l owns output slots 4l..4l+3 of the current pixel; a warp streams its 16 pixels ----
+  // ---- D. maps: lane l owns output slots 4l..4l+3 of the current pixel; a warp streams its 16 pixels.
+  // List entries between a pixel's hit count and the next multiple of 4 point at the sentinel candidate
+  // (id -> -1, z = -1), so a lane either gathers four entries unconditionally or stores the -1 padding.
   if (q.idx || q.zbuf || q.dist2) {
     const int32_t base = (int32_t)((size_t)b * P);
+    const int k0 = 4 * lane;
+    const bool vec = (K & 3) == 0;
     for (int j = 0; j < 16; ++j) {
       if (!__shfl_sync(FULL, (int)inimg, 2 * j)) continue;
       const int pj = warp * 16 + j;
       const int nhj = __shfl_sync(FULL, nh, 2 * j);
-      const float xfj = sm.ndcx[pj & 7], yfj = sm.ndcy[pj >> 3];
-      const int pxi = tx * TILE + (pj & 7), pyi = ty * TILE + (pj >> 3);
       int id4[4] = {-1, -1, -1, -1};
       float z4[4] = {-1.f, -1.f, -1.f, -1.f}, d4[4] = {-1.f, -1.f, -1.f, -1.f};
-      const int k0 = 4 * lane;
       if (k0 < nhj) {
+        const float xfj = sm.ndcx[pj & 7], yfj = sm.ndcy[pj >> 3];
         const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pj][k0]);
-        const unsigned short ls[4] = {(unsigned short)(L.x & 0xffffu), (unsigned short)(L.x >> 16),
-                                      (unsigned short)(L.y & 0xffffu), (unsigned short)(L.y >> 16)};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (k0 + e < nhj) {
-            const Cand cd = sm.cand[ls[e]];
-            id4[e] = base + cd.id;
-            z4[e] = cd.z;
-            d4[e] = dist2_rn(__fsub_rn(cd.x, xfj), __fsub_rn(cd.y, yfj));
-          }
+        const Cand c0 = sm.cand[L.x & 0xffffu], c1 = sm.cand[L.x >> 16];
+        const Cand c2 = sm.cand[L.y & 0xffffu], c3 = sm.cand[L.y >> 16];
+        id4[0] = base + c0.id;
+        id4[1] = base + c1.id;
+        id4[2] = base + c2.id;
+        id4[3] = base + c3.id;
+        z4[0] = c0.z;
+        z4[1] = c1.z;
+        z4[2] = c2.z;
+        z4[3] = c3.z;
+        d4[0] = dist2_rn(__fsub_rn(c0.x, xfj), __fsub_rn(c0.y, yfj));
+        const float e1 = dist2_rn(__fsub_rn(c1.x, xfj), __fsub_rn(c1.y, yfj));
+        const float e2 = dist2_rn(__fsub_rn(c2.x, xfj), __fsub_rn(c2.y, yfj));
+        const float e3 = dist2_rn(__fsub_rn(c3.x, xfj), __fsub_rn(c3.y, yfj));
+        d4[1] = (k0 + 1 < nhj) ? e1 : -1.0f;  // slot k0 itself is always a real hit here
+        d4[2] = (k0 + 2 < nhj) ? e2 : -1.0f;
+        d4[3] = (k0 + 3 < nhj) ? e3 : -1.0f;
       }
-      store_slots(q, ((size_t)b * S + pyi) * S + pxi, lane, id4, z4, d4);
+      if (k0 < K) {
+        const size_t o = (((size_t)b * S + (ty * TILE + (pj >> 3))) * S + tx * TILE + (pj & 7)) * K + k0;
+        if (vec) {
+          if (q.idx) __stcs(reinterpret_cast<int4*>(q.idx + o), make_int4(id4[0], id4[1], id4[2], id4[3]));
+          if (q.zbuf) __stcs(reinterpret_cast<float4*>(q.zbuf + o), make_float4(z4[0], z4[1], z4[2], z4[3]));
+          if (q.dist2) __stcs(reinterpret_cast<float4*>(q.dist2 + o), make_float4(d4[0], d4[1], d4[2], d4[3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (k0 + e < K) {
+              if (q.idx) q.idx[o + e] = id4[e];
+              if (q.zbuf) q.zbuf[o + e] = z4[e];
+              if (q.dist2) q.dist2[o + e] = d4[e];
+            }
+        }
+      }
     }
   }
 }

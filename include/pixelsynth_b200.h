@@ -96,6 +96,61 @@ int ps_splat_fwd(const float* depth, const float* feat, const float* mats, int B
 long long ps_launch_count(void);
 void ps_launch_count_reset(void);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense convolution as a TMA + tcgen05 implicit GEMM (bf16 operands, fp32 accumulation in TMEM).
+ * Replaces the cuDNN convolutions behind nn.Conv2d / nn.ConvTranspose2d of the reference's inference
+ * networks: Unet (models/networks/architectures.py:191-209,230-279), ResNet_Block of the refinement
+ * decoder (models/layers/blocks.py:41-74), VQ-VAE-2 Encoder / Decoder (models/vqvae2/vqvae.py:80-161).
+ * Activations are NHWC bf16 with the channel count a multiple of 8.  The convolution is described as a list
+ * of taps per input tensor: output pixel (oy, ox) reads input pixel (oy*stride + dy[t], ox*stride + dx[t])
+ * (out-of-image reads are zero) against rows wrow[t] .. wrow[t]+cout_pad-1 of the packed weight matrix
+ * [w_rows][w_cin_pad] (bf16, input channels contiguous, zero padded to a multiple of 64).  A second input with
+ * its own taps accumulates into the same output (the decoder's fused 1x1 skip convolution).
+ * Epilogue: v = acc + bias[c] (+ residual); output o = act_o(v * scale_o[c] + shift_o[c]) for up to two NHWC
+ * bf16 outputs (channel stride / offset allow writing into a concatenation buffer) and an optional fp32 NCHW
+ * copy of output 0.  Output pixel (oy, ox) is stored at (oy*out_sy + out_py, ox*out_sx + out_px) of an
+ * out_H x out_W image (the four phases of a stride-2 transposed convolution).
+ * ------------------------------------------------------------------------------------------------ */
+#define PS_ACT_NONE 0
+#define PS_ACT_RELU 1
+#define PS_ACT_LEAKY02 2
+#define PS_ACT_TANH 3
+#define PS_ACT_SIGMOID_AFFINE 4 /* sigmoid(v) * act_param[0] + act_param[1] */
+#define PS_ACT_ELU 5
+
+typedef struct {
+  const void* ptr; /* NHWC bf16 */
+  int H, W, C, cstride;
+  int ntaps;
+  int dy[16], dx[16];
+  int wrow[16];
+} ps_conv_input;
+
+typedef struct {
+  void* ptr; /* NHWC bf16 or NULL */
+  const float* scale;
+  const float* shift;
+  int per_sample; /* scale/shift are [N][Cout] instead of [Cout] */
+  int act;
+  int cstride, coffset;
+} ps_conv_output;
+
+typedef struct {
+  ps_conv_input in[2];
+  const void* weights;
+  int w_rows, w_cin_pad;
+  int N, Hout, Wout, Cout, cout_pad, stride;
+  const float* bias;
+  const void* residual; /* NHWC bf16 on the full output grid */
+  int res_cstride;
+  ps_conv_output out[2];
+  float* out_f32_nchw;
+  float act_param[2];
+  int out_H, out_W, out_sy, out_sx, out_py, out_px; /* 0 = same as Hout/Wout, stride 1, phase 0 */
+} ps_conv_desc;
+
+int ps_conv_igemm(const ps_conv_desc* desc, void* stream);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels (currently
  * "fine_kernel") are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;

@@ -27,6 +27,7 @@ SIGNATURES = {
     "ps_splat_fwd_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_d]),
     "ps_splat_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_d, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p,
                            c_p, c_sz, c_p]),
+    "ps_conv_igemm": (c_i, [c_p, c_p]),
     "ps_launch_count": (ctypes.c_longlong, []),
     "ps_launch_count_reset": (None, []),
     "ps_timing_enable": (None, [c_i]),

@@ -151,6 +151,31 @@ typedef struct {
 
 int ps_conv_igemm(const ps_conv_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Memory-bound glue between the convolutions (csrc/elementwise.cu).
+ * ------------------------------------------------------------------------------------------------ */
+/* (N,C,H,W) f32 -> (N,H,W,cstride) bf16, zero padded; if mask (N,H,W u8) is given channel C = float(~mask):
+ * the decoder input torch.cat((x, (~background_mask).unsqueeze(1).float()), 1), architectures.py:154. */
+int ps_nchw_to_nhwc_bf16(const float* x, int N, int C, int H, int W, const uint8_t* mask, void* out, int cstride,
+                         void* stream);
+/* NHWC bf16 resampling with up to two outputs y = act(v*scale+shift): mode 0 identity, 1 nn.AvgPool2d(3,2,1)
+ * (blocks.py:46), 2 nn.Upsample(scale_factor=2, mode="bilinear") (blocks.py:48, architectures.py:201). */
+int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int mode, const ps_conv_output* out0,
+                const ps_conv_output* out1, void* stream);
+/* LinearNoiseLayer + bn in eval mode (normalization.py:39-47,146-171): per-sample scale/shift (N,cpad) such that
+ * bn(x, gain, bias) = x*scale + shift, from noise z (N,Z) and the spectrally normalised (C,Z) gain/bias matrices. */
+int ps_noise_affine(const float* z, int N, int Z, const float* Wg, const float* Wb, const float* mean, const float* var,
+                    float eps, int C, int cpad, float* scale, float* shift, void* stream);
+/* Quantize.forward's code search (vqvae.py:41-48): x (N,D,HW) f32, embed (D,J) -> ids (N,HW) int64. */
+int ps_vq_argmin(const float* x, int N, int D, int HW, const float* embed, int J, long long* ids, void* stream);
+/* Quantize.embed_code (vqvae.py:76-77) into NHWC bf16 (total, D). */
+int ps_embed_codes(const long long* ids, int total, int D, const float* embed, int J, void* out, void* stream);
+/* ZbufferModelPts.get_combined (z_buffermodel.py:703-708): a*(1-bg) + b*bg, NCHW f32, bg (N,HW) u8. */
+int ps_combine(const float* a, const float* b, const uint8_t* bg, int N, int C, int HW, float* out, void* stream);
+/* ResNetDecoder head (architectures.py:157-160): tanh(v + x), or tanh(v) + x when normalize_before_residual. */
+int ps_tanh_residual(const float* v, const float* x, long long n, int normalize_before_residual, float* out,
+                     void* stream);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels (currently
  * "fine_kernel") are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;

@@ -28,6 +28,13 @@ SIGNATURES = {
     "ps_splat_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_d, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p,
                            c_p, c_sz, c_p]),
     "ps_conv_igemm": (c_i, [c_p, c_p]),
+    "ps_nchw_to_nhwc_bf16": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p]),
+    "ps_resample": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "ps_noise_affine": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_i, c_p, c_p, c_p]),
+    "ps_vq_argmin": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p]),
+    "ps_embed_codes": (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p]),
+    "ps_combine": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "ps_tanh_residual": (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
     "ps_launch_count": (ctypes.c_longlong, []),
     "ps_launch_count_reset": (None, []),
     "ps_timing_enable": (None, [c_i]),

@@ -1,0 +1,305 @@
+// Memory-bound glue kernels between the tensor-core convolutions (all NHWC bf16 unless stated):
+//   layout conversion (+ the decoder's mask channel, architectures.py:154), AvgPool2d(3,2,1) / bilinear x2
+//   resampling with the next layer's noise-conditioned batch-norm + ReLU folded in (blocks.py:45-63,
+//   normalization.py:39-47,159-171), LinearNoiseLayer gain/bias (normalization.py:39-47), VQ nearest-code search and
+//   code embedding (vqvae.py:41-48,76-77), get_combined (z_buffermodel.py:703-708), tanh(residual) head
+//   (architectures.py:157-160).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ps {
+
+__device__ __forceinline__ float ew_act(float v, int act) {
+  switch (act) {
+    case PS_ACT_RELU: return fmaxf(v, 0.0f);
+    case PS_ACT_LEAKY02: return v > 0.0f ? v : 0.2f * v;
+    case PS_ACT_TANH: return tanhf(v);
+    case PS_ACT_ELU: return v > 0.0f ? v : expm1f(v);
+    default: return v;
+  }
+}
+
+// (N,C,H,W) f32 -> (N,H,W,cstride) bf16; channel C optionally receives mask ? 0 : 1 (float(~background_mask));
+// remaining channels are zeroed.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                                           const uint8_t* __restrict__ mask, __nv_bfloat16* __restrict__ out,
+                                                           int cstride) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * H * W;
+  if (pix >= total) return;
+  const size_t hw = (size_t)H * W;
+  const size_t n = pix / hw, r = pix - n * hw;
+  __nv_bfloat16* o = out + pix * cstride;
+  for (int c = 0; c < cstride; ++c) {
+    float v = 0.0f;
+    if (c < C)
+      v = x[(n * C + c) * hw + r];
+    else if (c == C && mask)
+      v = mask[pix] ? 0.0f : 1.0f;
+    o[c] = __float2bfloat16(v);
+  }
+}
+
+struct ResampleOut {
+  __nv_bfloat16* ptr;
+  const float* scale;
+  const float* shift;
+  int per_sample, act, cstride, coffset;
+};
+
+// mode 0: identity, 1: AvgPool2d(3, stride 2, pad 1, count_include_pad), 2: bilinear x2 (align_corners=False).
+// One thread per (output pixel, 8-channel group); up to two outputs y = act(v * scale + shift).
+__global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __restrict__ in, int N, int H, int W, int C,
+                                                       int in_cstride, int mode, int Ho, int Wo, ResampleOut o0,
+                                                       ResampleOut o1) {
+  const int groups = C >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  size_t pix = idx / groups;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((size_t)Wo * Ho));
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto accum = [&](int y, int x, float w) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * H + y) * W + x) * in_cstride + g * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      v[2 * j] += w * f.x;
+      v[2 * j + 1] += w * f.y;
+    }
+  };
+  if (mode == 0) {
+    accum(oy, ox, 1.0f);
+  } else if (mode == 1) {
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int y = 2 * oy + dy, x = 2 * ox + dx;
+        if (y >= 0 && y < H && x >= 0 && x < W) accum(y, x, 1.0f / 9.0f);
+      }
+  } else {
+    // PyTorch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) / 2 - 0.5 clamped at 0
+    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.0f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.0f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    accum(y0, x0, (1.0f - ly) * (1.0f - lx));
+    accum(y0, x1, (1.0f - ly) * lx);
+    accum(y1, x0, ly * (1.0f - lx));
+    accum(y1, x1, ly * lx);
+  }
+  const ResampleOut* outs[2] = {&o0, &o1};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const ResampleOut& o = *outs[k];
+    if (!o.ptr) continue;
+    const float* sc = o.scale ? o.scale + (o.per_sample ? (size_t)n * C : 0) + g * 8 : nullptr;
+    const float* sh = o.shift ? o.shift + (o.per_sample ? (size_t)n * C : 0) + g * 8 : nullptr;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j];
+      if (sc) t *= sc[j];
+      if (sh) t += sh[j];
+      y[j] = ew_act(t, o.act);
+    }
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(y[4], y[5]), h3 = __floats2bfloat162_rn(y[6], y[7]);
+    uint4 w;
+    w.x = *reinterpret_cast<uint32_t*>(&h0);
+    w.y = *reinterpret_cast<uint32_t*>(&h1);
+    w.z = *reinterpret_cast<uint32_t*>(&h2);
+    w.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(o.ptr + (((size_t)n * Ho + oy) * Wo + ox) * o.cstride + o.coffset + g * 8) = w;
+  }
+}
+
+// LinearNoiseLayer + bn (eval): gain = 1 + Wg z, bias = Wb z; scale = rsqrt(var + eps) * gain;
+// shift = bias - mean * scale   (fused_bn: x * scale - (mean * scale - bias)).  Wg, Wb: (C, Z) already divided
+// by their spectral norm.  Channels c >= C of the (N, cpad) outputs get scale 0 / shift 0.
+__global__ void noise_affine_kernel(const float* __restrict__ z, int N, int Z, const float* __restrict__ Wg,
+                                    const float* __restrict__ Wb, const float* __restrict__ mean,
+                                    const float* __restrict__ var, float eps, int C, int cpad, float* __restrict__ scale,
+                                    float* __restrict__ shift) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * cpad) return;
+  const int n = idx / cpad, c = idx - n * cpad;
+  float s = 0.0f, t = 0.0f;
+  if (c < C) {
+    float g = 0.0f, b = 0.0f;
+    for (int k = 0; k < Z; ++k) {
+      const float zk = z[n * Z + k];
+      g += Wg[c * Z + k] * zk;
+      b += Wb[c * Z + k] * zk;
+    }
+    s = rsqrtf(var[c] + eps) * (1.0f + g);
+    t = b - mean[c] * s;
+  }
+  scale[idx] = s;
+  shift[idx] = t;
+}
+
+// Nearest codebook entry: argmax_j -(|x|^2 - 2 x.E_j + |E_j|^2)  (vqvae.py:42-48).  x: (N, D, HW) fp32 (NCHW),
+// embed: (D, J).  One warp per pixel; ties resolve to the smallest j (torch.max returns the first maximum).
+__global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict__ x, int N, int D, int HW,
+                                                        const float* __restrict__ embed, int J,
+                                                        long long* __restrict__ ids) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N * HW) return;
+  const int n = warp / HW, r = warp - n * HW;
+  const float* xp = x + (size_t)n * D * HW + r;
+  float x2 = 0.0f;
+  for (int d = 0; d < D; ++d) {
+    const float v = xp[(size_t)d * HW];
+    x2 += v * v;
+  }
+  float best = -INFINITY;
+  int bj = 0x7fffffff;
+  for (int j = lane; j < J; j += 32) {
+    float dot = 0.0f, e2 = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      const float e = embed[(size_t)d * J + j];
+      dot += xp[(size_t)d * HW] * e;
+      e2 += e * e;
+    }
+    const float score = -(x2 - 2.0f * dot + e2);
+    if (score > best) {
+      best = score;
+      bj = j;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+    if (ob > best || (ob == best && oj < bj)) {
+      best = ob;
+      bj = oj;
+    }
+  }
+  if (lane == 0) ids[warp] = bj;
+}
+
+// embed_code: ids (N*HW) -> NHWC bf16 (N*HW, D) from embed (D, J)
+__global__ void embed_kernel(const long long* __restrict__ ids, int total, int D, const float* __restrict__ embed, int J,
+                             __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total * D) return;
+  const int p = idx / D, d = idx - p * D;
+  out[idx] = __float2bfloat16(embed[(size_t)d * J + (int)ids[p]]);
+}
+
+// get_combined: a * (1 - bg) + b * bg per pixel, NCHW f32, bg (N,H,W) u8
+__global__ void combine_kernel(const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ bg,
+                               int N, int C, int HW, float* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * C * HW) return;
+  const size_t n = idx / ((size_t)C * HW), r = idx % HW;
+  const float m = bg[n * HW + r] ? 1.0f : 0.0f;
+  out[idx] = a[idx] * (1.0f - m) + b[idx] * m;
+}
+
+// out = tanh(v + x) (predict_residual) or tanh(v) + x (normalize_before_residual), elementwise f32
+__global__ void tanh_residual_kernel(const float* __restrict__ v, const float* __restrict__ x, size_t n, int before,
+                                     float* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  out[idx] = before ? tanhf(v[idx]) + x[idx] : tanhf(v[idx] + x[idx]);
+}
+
+}  // namespace ps
+
+using namespace ps;
+
+extern "C" {
+
+int ps_nchw_to_nhwc_bf16(const float* x, int N, int C, int H, int W, const uint8_t* mask, void* out, int cstride,
+                         void* stream) {
+  PS_CHECK_ARG(x && out && N >= 0 && C >= 1 && H >= 1 && W >= 1 && cstride >= C + (mask ? 1 : 0));
+  const size_t total = (size_t)N * H * W;
+  if (total == 0) return PS_OK;
+  nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, N, C, H, W, mask,
+                                                                                        (__nv_bfloat16*)out, cstride);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int mode, const ps_conv_output* out0,
+                const ps_conv_output* out1, void* stream) {
+  PS_CHECK_ARG(in && out0 && N >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && in_cstride % 8 == 0);
+  PS_CHECK_ARG(mode >= 0 && mode <= 2);
+  const int Ho = mode == 1 ? (H + 1) / 2 : (mode == 2 ? 2 * H : H);
+  const int Wo = mode == 1 ? (W + 1) / 2 : (mode == 2 ? 2 * W : W);
+  ResampleOut o[2];
+  memset(o, 0, sizeof(o));
+  const ps_conv_output* src[2] = {out0, out1};
+  for (int k = 0; k < 2; ++k)
+    if (src[k] && src[k]->ptr) {
+      PS_CHECK_ARG(src[k]->cstride % 8 == 0 && src[k]->coffset % 8 == 0);
+      o[k].ptr = (__nv_bfloat16*)src[k]->ptr;
+      o[k].scale = src[k]->scale;
+      o[k].shift = src[k]->shift;
+      o[k].per_sample = src[k]->per_sample;
+      o[k].act = src[k]->act;
+      o[k].cstride = src[k]->cstride;
+      o[k].coffset = src[k]->coffset;
+    }
+  const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  if (total == 0) return PS_OK;
+  resample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, N, H, W, C, in_cstride, mode, Ho, Wo, o[0], o[1]);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_noise_affine(const float* z, int N, int Z, const float* Wg, const float* Wb, const float* mean, const float* var,
+                    float eps, int C, int cpad, float* scale, float* shift, void* stream) {
+  PS_CHECK_ARG(z && Wg && Wb && mean && var && scale && shift && N >= 1 && Z >= 1 && C >= 1 && cpad >= C);
+  const int total = N * cpad;
+  noise_affine_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(z, N, Z, Wg, Wb, mean, var, eps, C, cpad,
+                                                                             scale, shift);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_vq_argmin(const float* x, int N, int D, int HW, const float* embed, int J, long long* ids, void* stream) {
+  PS_CHECK_ARG(x && embed && ids && N >= 0 && D >= 1 && HW >= 1 && J >= 1);
+  const size_t warps = (size_t)N * HW;
+  if (warps == 0) return PS_OK;
+  vq_argmin_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, N, D, HW, embed, J, ids);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_embed_codes(const long long* ids, int total, int D, const float* embed, int J, void* out, void* stream) {
+  PS_CHECK_ARG(ids && embed && out && total >= 0 && D >= 1 && J >= 1);
+  if (total == 0) return PS_OK;
+  embed_kernel<<<(total * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ids, total, D, embed, J, (__nv_bfloat16*)out);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_combine(const float* a, const float* b, const uint8_t* bg, int N, int C, int HW, float* out, void* stream) {
+  PS_CHECK_ARG(a && b && bg && out && N >= 0 && C >= 1 && HW >= 1);
+  const size_t total = (size_t)N * C * HW;
+  if (total == 0) return PS_OK;
+  combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, bg, N, C, HW, out);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_tanh_residual(const float* v, const float* x, long long n, int normalize_before_residual, float* out,
+                     void* stream) {
+  PS_CHECK_ARG(v && x && out && n >= 0);
+  if (n == 0) return PS_OK;
+  tanh_residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v, x, (size_t)n,
+                                                                                      normalize_before_residual, out);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+}  // extern "C"

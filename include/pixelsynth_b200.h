@@ -176,6 +176,21 @@ int ps_combine(const float* a, const float* b, const uint8_t* bg, int N, int C, 
 int ps_tanh_residual(const float* v, const float* x, long long n, int normalize_before_residual, float* out,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Generation order and locally-masked-convolution masks (native host code, csrc/glue.cu).  Replaces
+ * ZbufferModelPts.get_masks_for_batch (models/z_buffermodel.py:641-701): AvgPool8 + uint8 truncation,
+ * cv2.distanceTransform(DIST_L2, 5) x2, int(fd - bd), get_custom_order.pyx custom_idx and
+ * masking.get_masks.  ALL POINTERS ARE HOST POINTERS.
+ *   bg_mask_host (B,S,S) u8, S = 256           the splat's background mask
+ *   dist_host    (B,32,32) i32 or NULL          `distances`
+ *   order_host   (B,1024) i32                   generation order as cell index r*32+c
+ *   words_host   (B,3,1024) u16                 nine-bit tap masks per cell: [A dil 1, B dil 1, B dil 2],
+ *                                               bit t = (dr+1)*3+(dc+1) (F.unfold's tap order)
+ *   sample_mask_host (B,32,32) u8               cells to sample: all 64 pixels background (sample.py:29)
+ * ------------------------------------------------------------------------------------------------ */
+int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, int* dist_host, int* order_host,
+                        uint16_t* words_host, uint8_t* sample_mask_host);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels (currently
  * "fine_kernel") are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ps_embed_codes": (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p]),
     "ps_combine": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "ps_tanh_residual": (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
+    "ps_lmconv_glue_host": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "ps_launch_count": (ctypes.c_longlong, []),
     "ps_launch_count_reset": (None, []),
     "ps_timing_enable": (None, [c_i]),

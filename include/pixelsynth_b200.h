@@ -191,6 +191,40 @@ int ps_tanh_residual(const float* v, const float* x, long long n, int normalize_
 int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, int* dist_host, int* order_host,
                         uint16_t* words_host, uint8_t* sample_mask_host);
 
+/* ------------------------------------------------------------------------------------------------
+ * Activation-cached autoregressive sampler of the locally-masked-convolution PixelCNN (csrc/lmconv.cu).
+ * Replaces models/lmconv/sample.py:8-73 (sample) + models/lmconv/model.py:110-155 (OurPixelCNN.forward, called
+ * once per token there).  Weights: one bf16 array holding every layer as [tap][cin][cout] (masked 3x3 convs; nin
+ * layers are a single tap with the weight-norm g*v/|v| already applied) and one fp32 bias array; offsets below are
+ * element offsets into them.  ops lists the 18 column operations after u_init in execution order (14 gated
+ * resnets, kind 0; 4 dilated convs + PONO, kind 1) with the ids (0..32) of the cached tensors they read / write.
+ *   order (B,1024) i32, words (B,3,1024) u16, sample_mask (B,1024) u8: as produced by ps_lmconv_glue_host
+ *   codes (B,1024) i64: in = known codes, out = sampled cells filled (sample != 0)
+ *   uniforms (B,stride) f32: the k-th sampled cell of image b takes the first class whose cumulative
+ *            softmax(logits/temperature) exceeds uniforms[b][k]
+ *   nsteps (B) i32: cells of the generation order to process (everything after the last sampled cell is skipped)
+ *   logits_out (B,1024,512) f32 or NULL: logits of every processed cell (teacher-forced parity surface)
+ *   cache: ps_lmconv_cache_bytes(B) bytes of device scratch (the activation cache)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int kind;
+  int og, a, mid, out;
+  int w_in, b_in, w_skip, b_skip, w_out, b_out;
+} ps_lmconv_op;
+
+typedef struct {
+  const void* weights; /* bf16 */
+  const float* bias;
+  int w_uinit, b_uinit, w_nin, b_nin;
+  ps_lmconv_op ops[18];
+} ps_lmconv_weights;
+
+size_t ps_lmconv_cache_bytes(int B);
+int ps_lmconv_sample(const ps_lmconv_weights* w, int B, const int* order, const uint16_t* words,
+                     const uint8_t* sample_mask, long long* codes, const float* uniforms, int uniforms_stride,
+                     float temperature, const int* nsteps, int sample, float* logits_out, void* cache,
+                     size_t cache_bytes, void* stream);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels (currently
  * "fine_kernel") are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;

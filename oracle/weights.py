@@ -87,6 +87,10 @@ def make_state(net, seed=0, gain=1.0):
     sd = {k: sd[k] for k in table}
     if net == "vqvae":
         _calibrate_codebook(sd, g)
+    if net == "lmconv":
+        # a trained prior is peaked; with unit-scale logits over 512 classes every draw would sit on a near-uniform
+        # CDF where a 1e-3 logit error already moves the token.  Sharpen the output layer (logit std ~6).
+        sd["nin_out.lin_a.weight_g"] = sd["nin_out.lin_a.weight_g"] * 6.0
     if net == "unet":
         # the depth head sees sigmoid(): widen its pre-activation (std ~1.5) so predicted depth really varies.
         # weight_orig / sigma is scale invariant, so the knob is the stored u vector (sigma = u . W v).

@@ -1,0 +1,210 @@
+"""Mirror of reference models/z_buffermodel.py:29-419 (ZbufferModelPts), inference path only.
+
+Same constructor / forward(batch, netD=None) contract and output keys; every callee on the hot path dispatches to
+the sm_100a kernels of libpixelsynth_b200.so:
+  pts_regressor  -> nets.UnetB200                 (z_buffermodel.py:41-42, 304-308)
+  pts_transformer-> models.projection.PtsManipulator (splat kernels)            (:49-52, 323-332)
+  get_masks_for_batch -> lmconv.glue_host (native host code)                    (:641-701)
+  vqvae          -> nets.VQVAETopB200                                            (:82, 345, 250)
+  sample(outpaint2, ...) -> lmconv.LmconvB200.sample (activation-cached kernel) (:62-74, 246-247)
+  get_combined   -> ps_combine                                                   (:703-708)
+  projector      -> nets.ResNetDecoderB200                                       (:87, 252)
+Weights: a state dict with the reference's key names (`pts_regressor.*`, `vqvae.*`, `outpaint2.*`, `projector.*`;
+`module.` / `model.module.` prefixes of DataParallel checkpoints are stripped, demo.py:202-229).  Without a state
+dict the networks are random-initialised from opt.seed (pixelsynth_b200/synthetic.py): no checkpoint of the
+reference is reachable offline.
+Out of scope here: ranking num_samples > 1 candidates with the discriminator and the places365
+classifier (z_buffermodel.py:244-276) -- `ranker` may be supplied by the caller; default keeps sample 0.
+Stochastic elements are explicit: `noise` (decoder, 16 x (B,20)) and `uniforms` (sampler) can be injected; when
+absent they are drawn from torch generators seeded as the reference seeds its sampler (sample.py:14-16)."""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, lmconv, nets, synthetic
+from .._lib import check
+from . import _ops_loaded  # noqa: F401
+from .projection.z_buffer_manipulator import PtsManipulator
+
+ROTVECS = {"R": np.array([0, .6, 0]), "L": np.array([0, -.6, 0]), "U": np.array([-.3, 0, 0]), "D": np.array([.3, 0, 0]),
+           "UR": np.array([-.15, .3, 0]), "UL": np.array([-.15, -.3, 0]), "DR": np.array([.15, .3, 0]),
+           "DL": np.array([.15, -.3, 0])}  # z_buffermodel.py:112-113
+
+
+def _get(opt, name, default=None):
+    return getattr(opt, name, default) if not isinstance(opt, dict) else opt.get(name, default)
+
+
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def strip_parallel_prefixes(sd):
+    out = {}
+    for k, v in sd.items():
+        for p in ("model.module.", "module.", "model."):
+            if k.startswith(p):
+                k = k[len(p):]
+                break
+        out[k] = v
+    return out
+
+
+def euler_to_matrix(theta):
+    """z_buffermodel.py:186-200: R = Rz . Ry . Rx, float64."""
+    cx, sx, cy, sy, cz, sz = math.cos(theta[0]), math.sin(theta[0]), math.cos(theta[1]), math.sin(theta[1]), \
+        math.cos(theta[2]), math.sin(theta[2])
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return rz @ (ry @ rx)
+
+
+class ZbufferModelPts(nn.Module):
+    def __init__(self, opt, state_dict=None, device="cuda"):
+        super().__init__()
+        self.opt = opt
+        self.device = device
+        seed = int(_get(opt, "seed", 0) or 0)
+        if state_dict is None:
+            parts = {"pts_regressor.": synthetic.make_state("unet", seed), "vqvae.": synthetic.make_state("vqvae", seed),
+                     "outpaint2.": synthetic.make_state("lmconv", seed), "projector.": synthetic.make_state("decoder", seed)}
+            state_dict = {p + k: v for p, sd in parts.items() for k, v in sd.items()}
+        sd = strip_parallel_prefixes(state_dict)
+        self.pts_regressor = nets.UnetB200(_sub(sd, "pts_regressor."), device)
+        self.pts_transformer = PtsManipulator(_get(opt, "W", 256), C=3, opt=opt).to(device)
+        self.vqvae = nets.VQVAETopB200(_sub(sd, "vqvae."), device)
+        self.outpaint2 = lmconv.LmconvB200(_sub(sd, "outpaint2."), device)
+        self.projector = nets.ResNetDecoderB200(_sub(sd, "projector."), device,
+                                                bool(_get(opt, "normalize_before_residual", False)))
+        self.obs = [3, 32, 32]
+        self.ranker = None
+
+    # -- z_buffermodel.py:120-184 ---------------------------------------------------------------
+    def process_batch(self, batch):
+        cam = batch["cameras"][0]
+        dev = self.device
+        f = lambda t: t.to(dev, non_blocking=True).float()
+        out = [f(cam["K"]), f(cam["Kinv"]), f(cam["P"]), f(cam["Pinv"])]
+        if _get(self.opt, "model_setting") in ("train", "gen_paired_img"):
+            out += [f(batch["cameras"][-1]["P"]), f(batch["cameras"][-1]["Pinv"]), f(batch["images"][0]),
+                    f(batch["images"][-1])]
+        else:
+            out += [f(batch["images"][0])]
+        return out
+
+    # -- z_buffermodel.py:202-242 ---------------------------------------------------------------
+    def get_rt_from_rot(self, direction, input_RT, num=None, denom=None):
+        num = 0 if num is None else num
+        setting = _get(self.opt, "model_setting")
+        if setting in ("gen_two_imgs", "gen_scene"):
+            if direction == "S":
+                new_rt = input_RT.clone()
+                new_rt[:, 3, :] = 0
+                new_rt[:, 3, 3] = 1
+                t = .35 * torch.tensor([np.sin(2 * np.pi * num / denom), np.cos(2 * np.pi * num / denom),
+                                        .4 * np.sin(2 * np.pi * (.25 + num / denom))]).to(input_RT)
+                new_rt[:, :3, 3] = input_RT[:, :3, 3] + t
+                return torch.inverse(new_rt), new_rt
+            if direction == "C":
+                rotvec = np.array([0.2 * np.cos(2 * np.pi * num / denom), 0.2 * np.sin(2 * np.pi * num / denom), 0])
+            else:
+                rotvec = ROTVECS[direction] * num / denom
+        else:
+            rotvec = ROTVECS[direction] * _get(self.opt, "rotation") / np.linalg.norm(ROTVECS[direction])
+        mtx = torch.zeros(1, 4, 4, device=input_RT.device)
+        mtx[0, 3, 3] = 1
+        mtx[0, :3, :3] = torch.tensor(euler_to_matrix(rotvec)).to(torch.float32)
+        if _get(self.opt, "homography", False) and direction not in ("S", "C"):
+            new_rt = torch.zeros_like(input_RT)
+            new_rt[:, :, 3] = input_RT[:, :, 3]
+            new_rt[:, :3, :3] = mtx[:, :3, :3] @ input_RT[:, :3, :3]
+        else:
+            new_rt = mtx @ input_RT
+        return torch.inverse(new_rt), new_rt
+
+    def get_masks_for_batch(self, output_RT, input_RTinv, background_mask):
+        """-> (dist, order, words, sample_mask) numpy arrays; the reference's three float mask tensors of shape
+        (B*513|160|80, 9, 1024) are the nine-bit words[:, 0|1|2] here."""
+        return lmconv.glue_host(background_mask)
+
+    def get_combined(self, gen_fs, ar_sample, background_mask):
+        b, c, h, w = gen_fs.shape
+        out = torch.empty_like(gen_fs)
+        m = background_mask.contiguous().view(torch.uint8)
+        check(_lib.lib().ps_combine(gen_fs.contiguous().data_ptr(), ar_sample.contiguous().data_ptr(), m.data_ptr(), b, c,
+                                    h * w, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "ps_combine")
+        return out
+
+    def _sampler_uniforms(self, seed, B):
+        # sample.py:14-16 seeds numpy and torch from the sample index; the categorical draws themselves are explicit
+        # uniforms here (torch.multinomial's CUDA stream cannot be reproduced by another kernel)
+        np.random.seed(seed)
+        g = torch.Generator().manual_seed(seed * 10 + int(np.random.randint(188)))
+        return torch.rand(B, 1024, generator=g)
+
+    def get_best_sample(self, order, words, sample_mask, codes, background_mask, gen_fs, netD, input_img, noise=None,
+                        uniforms=None):
+        imgs = []
+        n = int(_get(self.opt, "num_samples", 1) or 1)
+        B = codes.shape[0]
+        for i in range(n):
+            u = uniforms if uniforms is not None else self._sampler_uniforms(i, B)
+            sampled = self.outpaint2.sample(codes, order, words, sample_mask, u, float(_get(self.opt, "temperature", 1.0)))
+            ar_sample = self.vqvae.decode_code(sampled)
+            combined = self.get_combined(gen_fs, ar_sample, background_mask)
+            imgs.append(self.projector.forward(combined, background_mask, noise))
+        if n == 1:
+            return imgs[0]
+        if self.ranker is None:
+            return imgs[0]  # discriminator + classifier ranking (z_buffermodel.py:254-276) is a "next" row
+        return imgs[int(self.ranker(imgs, input_img))]
+
+    # -- z_buffermodel.py:291-419 ---------------------------------------------------------------
+    def forward_image(self, batch, netD=None, noise=None, uniforms=None):
+        setting = _get(self.opt, "model_setting")
+        if setting in ("train", "gen_paired_img"):
+            K, K_inv, input_RT, input_RTinv, output_RT, output_RTinv, input_img, output_img = self.process_batch(batch)
+            if setting == "train":
+                raise NotImplementedError("training is out of scope (SURVEY.md section 2)")
+        else:
+            K, K_inv, input_RT, input_RTinv, input_img = self.process_batch(batch)
+            output_RTinv, output_RT = self.get_rt_from_rot(_get(self.opt, "direction"), input_RT)
+            output_img = None
+        if _get(self.opt, "use_gt_depth", False):
+            raise NotImplementedError("use_gt_depth: the shipped configuration predicts depth")
+        min_z, max_z = float(_get(self.opt, "min_z")), float(_get(self.opt, "max_z"))
+        if _get(self.opt, "use_inverse_depth", False):
+            raise NotImplementedError("use_inverse_depth is not used by the shipped configuration")
+        regressed_pts = self.pts_regressor.forward(input_img, min_z, max_z)
+        if not _get(self.opt, "use_rgb_features", True):
+            raise NotImplementedError("the shipped configuration splats RGB (use_rgb_features)")
+        B = input_img.shape[0]
+        if output_RT.shape[0] != B:
+            output_RT, output_RTinv = output_RT.expand(B, 4, 4), output_RTinv.expand(B, 4, 4)
+        gen_fs, background_mask = self.pts_transformer.forward_justpts(
+            input_img, regressed_pts, K, K_inv, input_RT, input_RTinv, output_RT.contiguous(), output_RTinv.contiguous())
+        if _get(self.opt, "no_outpainting", False):
+            raise NotImplementedError("no_outpainting (3-channel decoder, SynSin baseline) is not the shipped configuration")
+        else:
+            _, order, words, sample_mask = self.get_masks_for_batch(output_RT, input_RTinv, background_mask)
+            codes = self.vqvae.encode_top(gen_fs)
+            gen_img = self.get_best_sample(order, words, sample_mask, codes, background_mask, gen_fs, netD, input_img,
+                                           noise, uniforms)
+            self.last = dict(depth=regressed_pts, gen_fs=gen_fs, background_mask=background_mask, order=order, words=words,
+                             sample_mask=sample_mask, codes=codes, output_RT=output_RT)
+        outputs = {"InputImg": input_img, "PredImg": gen_img, "PredDepthImg": regressed_pts / 5 - 1,
+                   "ForegroundImg": (~background_mask).repeat(B, 1, 1, 1).float()}   # shape quirk kept (:389)
+        if output_img is not None:
+            outputs["OutputImg"] = output_img
+        outputs["FeaturesImg"] = gen_fs
+        loss = {}  # the reference computes loss_function(gen_img, gen_img) here and discards it (:412-414)
+        return loss, outputs
+
+    def forward(self, batch, netD=None, **kw):
+        setting = _get(self.opt, "model_setting")
+        if setting == "gen_scene":
+            raise NotImplementedError("gen_scene (cumulative cloud sweep) is a 'next' row of SURVEY.md 8f")
+        return self.forward_image(batch, netD, **kw)

@@ -1,4 +1,4 @@
-"""Dumps parameter/buffer names and shapes of the reference's inference networks to tests/golden/state_shapes.json
+"""Dumps parameter/buffer names and shapes of the reference's inference networks to pixelsynth_b200/data/state_shapes.json
 (run in the build container only; needs /root/reference).  The seeded weight factory (oracle/weights.py) fills
 these shapes, so the same state dicts load -- strictly -- into the reference's own modules."""
 import json
@@ -34,7 +34,7 @@ def main():
     }
     out = {k: {n: [list(t.shape), str(t.dtype).replace("torch.", "")] for n, t in m.state_dict().items()}
            for k, m in nets.items()}
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "state_shapes.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "pixelsynth_b200", "data", "state_shapes.json")
     json.dump(out, open(path, "w"), indent=0, sort_keys=False)
     for k, v in out.items():
         print(k, len(v), "tensors", sum(int(torch.tensor(s[0]).prod()) if s[0] else 1 for s in v.values()), "elements")

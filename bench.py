@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- novel views/sec (256x256) of the pixelsynth_b200 hot path, with roofline and CPU baseline.
+"""bench.py -- novel views/sec (256x256) of the pixelsynth_b200 hot path, with rooflines and a CPU baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
 
-Contract (see DESIGN.md "Measurement"): one JSON line on stdout from rank 0.
-  step      = one pass of the hot path over one batch of B synthetic 256x256 source images (RGB U[-1,1],
-              depth U[min_z,max_z], circle-translation target cameras of z_buffermodel.py:214), each -> one view.
-  value     = views/s with inputs resident in HBM, CUDA events on the launching stream, max over ranks.
-  e2e       = the same through the reference-facing call (PtsManipulator.forward_justpts) with HOST pinned
-              buffers: H2D of depth+features+cameras and D2H of the image+mask inside the timed region.
-  roofline  = the dominant kernel (fine_kernel) timed alone with CUDA events; algorithmic bytes per launch
-              = 69 009 408 B/view x B over the measured HBM peak (MEASURED_PEAKS.json).
-  cpu_baseline = the CPU oracle (port of the reference algorithm) on a bounded sample, rank 0, N=1 only.
---impl reference times the CPU oracle with all host threads on the same workload (rank 0 only).
+One JSON line on stdout from rank 0 (contract in DESIGN.md section 7).
+  workload  = BASELINE.json configs[1]: the demo path `ZbufferModelPts.forward` (models/z_buffermodel.py:291-419) --
+              depth U-Net -> z-buffer splat -> order/masks -> VQ-VAE-2 encode -> lmconv autoregressive outpaint ->
+              VQ-VAE-2 decode -> refinement decoder -- on synthetic 256x256 images, one novel view per image, batched
+              B images per step (the path is embarrassingly parallel over images).  Seeded random weights of the
+              reference's architecture (no checkpoint is reachable offline).
+  value     = views/s with the inputs resident in HBM; CUDA events on the launching stream; max over ranks.
+  e2e       = views/s through BaseModel.__call__ (models/base_model.py:93-103) with HOST pinned inputs: H2D of
+              images + cameras and D2H of PredImg inside the timed region.
+  roofline  = the dominant kernel of the step (by summed device time, measured with CUDA events the library records
+              on the launching stream); `rooflines` lists splat (HBM), sampler and convolutions (tensor).
+  cpu_baseline / --impl reference = the CPU oracle of the same path (fp32 torch restatement of the reference's
+              modules + the C splat oracle); the sampler is timed reference-style (one full forward per token,
+              models/lmconv/sample.py:54-66) on a few tokens and extrapolated linearly -- stated in `sample`.
 Nothing here reads /root/reference.
 """
 import argparse
@@ -22,6 +26,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -30,9 +35,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W = 256
 K_PP = 128
 RADIUS = 4.0
-C = 3
-BYTES_PER_VIEW_MAPS = 4 * W * W + 4 * C * W * W + 4 * C * W * W + W * W + 2 * 4 * K_PP * W * W  # 69 009 408
-BYTES_PER_VIEW_FUSED = 4 * W * W + 4 * C * W * W + 4 * C * W * W + W * W                        # 1 900 544
+BYTES_PER_VIEW_SPLAT_FUSED = 4 * W * W + 2 * 4 * 3 * W * W + W * W  # depth + feat in, image + mask out = 1 900 544
+FLOP_PER_CELL = 11.163e6       # lmconv column, SURVEY.md 8d
+FLOP_DECODER = 128.22e9        # ResNetDecoder per image
+FLOP_UNET, FLOP_VQ_ENC, FLOP_VQ_DEC = 5.53e9, 3.66e9 + 0.07e9, 2.58e9
 METRIC = "novel views/sec (256x256)"
 UNIT = "views/s"
 
@@ -40,51 +46,56 @@ UNIT = "views/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="views per step per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=16, help="views in the cpu_baseline sample")
+    ap.add_argument("--batch", type=int, default=32, help="images (= views) per step per GPU")
+    ap.add_argument("--cpu-tokens", type=int, default=4, help="sampler tokens timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
+def make_opt(**kw):
+    o = dict(W=256, splatter="xyblending", learn_default_feature=True, radius=RADIUS, pp_pixel=K_PP, rad_pow=2, tau=1.0,
+             accumulation="alphacomposite", background_smoothing_kernel_size=13, min_z=0.5, max_z=10.0,
+             use_rgb_features=True, use_gt_depth=False, use_inverse_depth=False, depth_predictor_type="unet",
+             no_outpainting=False, vqvae=True, num_samples=1, temperature=0.7, model_setting="gen_paired_img",
+             direction="L", rotation=0.6, homography=False, seed=0, normalize_image=True, predict_residual=True,
+             normalize_before_residual=False, refine_model_type="resnet_256W8UpDown3", ngf=64, norm_G="sync:spectral_batch")
+    o.update(kw)
+    return types.SimpleNamespace(**o)
+
+
 def workload_config(args, world):
     return {
-        "workload": "z-buffer splat stage (SURVEY 8a S1-S5: unproject -> camera transform -> K-nearest rasterise -> "
-                    "alpha composite -> background mask) of BASELINE configs[1], 256x256, P=65536, K=128, radius 4 px; "
-                    "value/roofline with idx+zbuf maps emitted (69.0 MB/view, the bit-exact parity surface), e2e "
-                    "through PtsManipulator.forward_justpts (image+mask only). Depth Unet / VQ-VAE / lmconv / "
-                    "refinement stages are not in this number yet.",
-        "views_per_step_per_gpu": args.batch,
-        "global_views_per_step": args.batch * world,
-        "image": "256x256", "points_per_pixel": K_PP, "radius_px": RADIUS,
-        "target_cameras": "translation circle n=rank%8 (create_nerf_like_circles.py:14)",
-        "l2_policy": "outputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush" %
-                     (BYTES_PER_VIEW_MAPS * args.batch / 1e6),
-        "parallelism": "views sharded across ranks, one NCCL broadcast of the sources at job start" if world > 1
+        "workload": "BASELINE configs[1] (demo path: depth Unet -> splat -> order/masks -> VQ-VAE-2 encode -> lmconv "
+                    "outpaint -> VQ-VAE-2 decode -> refinement decoder), one novel 256x256 view per synthetic image, "
+                    "target = translation-circle camera n = rank mod 8 (create_nerf_like_circles.py:14), num_samples 1, "
+                    "temperature 0.7, batched %d images per step per GPU" % args.batch,
+        "views_per_step_per_gpu": args.batch, "global_views_per_step": args.batch * world,
+        "weights": "seeded random init of the reference architecture (pixelsynth_b200/synthetic.py)",
+        "l2_policy": "activations + sampler cache per step (> 1 GB at batch 32) exceed the 126 MB L2; no explicit flush",
+        "parallelism": "images sharded across ranks; one NCCL broadcast of the source images at job start" if world > 1
                        else "single GPU",
     }
 
 
-def make_inputs(B, view, seed=0):
-    import numpy as np
-    from util import demo_cameras, pack_mats
+def make_batch(B, view, seed=0):
+    import torch
+    from util import demo_cameras
+    from pixelsynth_b200 import synthetic
 
-    rng = np.random.default_rng(seed)
-    depth = rng.uniform(0.5, 10.0, (B, 1, W, W)).astype(np.float32)
-    feat = rng.uniform(-1, 1, (B, C, W, W)).astype(np.float32)
-    cams = demo_cameras(B, "translate", seed, views=[view] * B)
-    return depth, feat, cams, pack_mats(*cams)
+    K, Kinv, RT1, RT1inv, RT2, RT2inv = [torch.from_numpy(m) for m in demo_cameras(B, "translate", seed, views=[view] * B)]
+    img = synthetic.synth_image(B, seed)
+    return {"images": [img, img.clone()],
+            "cameras": [{"K": K, "Kinv": Kinv, "P": RT1, "Pinv": RT1inv}, {"K": K, "Kinv": Kinv, "P": RT2, "Pinv": RT2inv}]}
 
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.rows = []
-        self.proc = None
-        self.index = index
+        self.rows, self.proc, self.index = [], None, index
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -94,8 +105,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
@@ -128,61 +138,91 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_peak():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+def peaks():
     try:
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json: copy GB/s, sustained bf16 TF/s)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_oracle_views_per_s(n_views, threads):
-    """Times the CPU oracle (oracle/splat_oracle.c, a port of the reference algorithm) on n_views views."""
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import splat_ref
+# ---------------------------------------------------------------------------------------------------------------
+# CPU oracle of the same path (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_oracle_view_seconds(n_tokens, threads, seed=0):
+    """One view through the CPU oracle; the sampler runs `n_tokens` reference-style steps and is extrapolated to the
+    view's sampled-cell count.  Returns (seconds per view, dict of stage seconds, sampled cells)."""
+    import numpy as np
+    import torch
+    from oracle import lmconv_ref, nets_ref, splat_ref
+    from pixelsynth_b200 import synthetic
+    from util import demo_cameras, pack_mats
 
-    splat_ref.build()
-    depth, feat, cams, mats = make_inputs(n_views, 0)
-    splat_ref.splat(depth[:1], feat[:1], mats[:1], W, K=K_PP, radius_px=RADIUS)  # warm-up
-
-    def one(i):
-        return splat_ref.splat(depth[i:i + 1], feat[i:i + 1], mats[i:i + 1], W, K=K_PP, radius_px=RADIUS)["out"].sum()
-
-    t0 = time.perf_counter()
-    if threads == 1:
-        for i in range(n_views):
-            one(i)
-    else:
-        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside the C oracle
-            list(ex.map(one, range(n_views)))
-    dt = time.perf_counter() - t0
-    return n_views / dt, dt
+    torch.set_num_threads(threads)
+    sds = {n: synthetic.make_state(n, 0) for n in ("unet", "vqvae", "lmconv", "decoder")}
+    img = synthetic.synth_image(1, seed)
+    cams = demo_cameras(1, "translate", seed, views=[0])
+    st = {}
+    with torch.no_grad():
+        t = time.perf_counter()
+        depth = nets_ref.unet_depth(sds["unet"], img, 0.5, 10.0)
+        st["unet"] = time.perf_counter() - t
+        t = time.perf_counter()
+        sp = splat_ref.splat(depth.numpy(), img.numpy(), pack_mats(*cams), W, K=K_PP, radius_px=RADIUS)
+        st["splat"] = time.perf_counter() - t
+        gen_fs, bg = torch.from_numpy(sp["out"]), torch.from_numpy(sp["bg"])
+        t = time.perf_counter()
+        _, orders, words, smask = lmconv_ref.glue_from_background(bg)
+        st["glue"] = time.perf_counter() - t
+        t = time.perf_counter()
+        ids, _ = nets_ref.vqvae_encode_top(sds["vqvae"], gen_fs)
+        st["vq_encode"] = time.perf_counter() - t
+        n_sampled = int(smask.sum())
+        t = time.perf_counter()
+        g = torch.Generator().manual_seed(1)
+        steps = max(1, min(n_tokens, n_sampled))
+        lmconv_ref.sample_reference_style(sds["lmconv"], ids, orders, words, smask.numpy(), torch.rand(1, 1024, generator=g), 0.7,
+                                          max_steps=steps)
+        per_token = (time.perf_counter() - t) / steps
+        st["lmconv_per_token"] = per_token
+        t = time.perf_counter()
+        ar = nets_ref.vqvae_decode_code(sds["vqvae"], ids)
+        st["vq_decode"] = time.perf_counter() - t
+        t = time.perf_counter()
+        comb = gen_fs * (~bg)[:, None].float() + ar * bg[:, None].float()
+        nets_ref.decoder_forward(sds["decoder"], comb, bg, [torch.randn(1, 20, generator=g) for _ in range(16)])
+        st["decoder"] = time.perf_counter() - t
+    total = sum(v for k, v in st.items() if k != "lmconv_per_token") + per_token * n_sampled
+    return total, st, n_sampled
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = max(threads, 8)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, dt = cpu_oracle_views_per_s(per_step, threads)
-        if i >= args.warmup:
-            vals.append((v, dt))
-        if sum(d for _, d in vals) > 150:
-            break
-    tot_t = sum(d for _, d in vals)
-    value = per_step * len(vals) / tot_t
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    secs = []
+    info = None
+    t_start = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        s, st, n_sampled = cpu_oracle_view_seconds(args.cpu_tokens, threads)
+        if i >= args.warmup:
+            secs.append(s)
+            info = (st, n_sampled)
+        if time.perf_counter() - t_start > 240 and secs:
+            break
+    value = len(secs) / sum(secs)
+    st, n_sampled = info
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / len(vals), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs),
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d views per step x %d steps of the same 256x256 K=128 splat workload, CPU oracle "
-                                   "(oracle/splat_oracle.c; PyTorch3D, the reference's rasteriser, is not installable "
-                                   "offline), %d host threads" % (per_step, len(vals), threads)},
+                         "sample": "1 view per step through the CPU oracle (torch fp32 restatement of the reference modules + "
+                                   "C splat oracle; the reference itself needs PyTorch3D CUDA ops and hard-coded .cuda()); "
+                                   "sampler timed reference-style on %d tokens (%.3f s/token) and extrapolated to the view's %d "
+                                   "sampled cells" % (args.cpu_tokens, st["lmconv_per_token"], n_sampled),
+                         "stage_seconds": st},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,7 +234,6 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -204,46 +243,33 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    devs = torch.device("cuda", local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=devs)
+        dist.init_process_group("nccl", device_id=dev)
 
-    import pixelsynth_b200.ops as ops  # registers torch.ops.pixelsynth_b200 (fails loudly if the .so is missing)
     from pixelsynth_b200 import _lib
-    from pixelsynth_b200.models.projection.z_buffer_manipulator import PtsManipulator
-    import types
+    from pixelsynth_b200.models.base_model import BaseModel
+    from pixelsynth_b200.models.z_buffermodel import ZbufferModelPts
+    from pixelsynth_b200.parallel import broadcast_sources
 
     L = _lib.lib()
     B = args.batch
-    view = rank % 8
-    depth, feat, cams, mats = make_inputs(B, view)
+    opt = make_opt()
+    model = ZbufferModelPts(opt, device=dev)
+    host_batch = make_batch(B, rank % 8)
 
-    # ---- job start: sources live on rank 0 and are broadcast once over NCCL ----
-    d_depth = torch.empty((B, 1, W, W), device=devs)
-    d_feat = torch.empty((B, C, W, W), device=devs)
-    bcast_ms = 0.0
-    if rank == 0:
-        d_depth.copy_(torch.from_numpy(depth))
-        d_feat.copy_(torch.from_numpy(feat))
-    if world > 1:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        dist.broadcast(d_depth, 0)
-        dist.broadcast(d_feat, 0)
-        e1.record()
-        torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-    d_mats = torch.from_numpy(mats).to(devs)
+    # ---- job start: the source images live on rank 0 and are broadcast once over NCCL ----
+    src = host_batch["images"][0].to(dev) if rank == 0 else torch.empty((B, 3, W, W), device=dev)
+    bcast_ms = broadcast_sources(src, world)
+    dev_batch = {"images": [src, src],
+                 "cameras": [{k: v.to(dev) for k, v in c.items()} for c in host_batch["cameras"]]}
+    g = torch.Generator().manual_seed(1 + rank)
+    noise = torch.randn(16, B, 20, generator=g).to(dev)
+    uniforms = torch.rand(B, 1024, generator=g)
 
-    def step_maps():
-        return torch.ops.pixelsynth_b200.splat(d_depth, d_feat, d_mats, W, W, K_PP, RADIUS, 1.0, 2, 0, 13, 1e-2, True,
-                                               False)
-
-    def step_fused():
-        return torch.ops.pixelsynth_b200.splat(d_depth, d_feat, d_mats, W, W, K_PP, RADIUS, 1.0, 2, 0, 13, 1e-2, False,
-                                               False)
+    def step_resident():
+        return model.forward(dev_batch, noise=noise, uniforms=uniforms)[1]["PredImg"]
 
     def barrier():
         if world > 1:
@@ -264,7 +290,7 @@ def main():
         ms = e0.elapsed_time(e1)
         launches = L.ps_launch_count()
         if world > 1:
-            t = torch.tensor([ms], device=devs)
+            t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, launches
@@ -272,85 +298,88 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_maps, launches = timed(step_maps, args.steps, args.warmup)
+    ms_res, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_fused, _ = timed(step_fused, args.steps, max(3, args.warmup))
 
-    # ---- e2e: reference-facing call with host buffers ----
-    opt = types.SimpleNamespace(splatter="xyblending", learn_default_feature=True, radius=RADIUS, pp_pixel=K_PP,
-                                rad_pow=2, tau=1.0, accumulation="alphacomposite", background_smoothing_kernel_size=13)
-    pm = PtsManipulator(W, C=C, opt=opt).to(devs)
-    h_depth = torch.from_numpy(depth).pin_memory()
-    h_feat = torch.from_numpy(feat).pin_memory()
-    h_cams = [torch.from_numpy(np.ascontiguousarray(m)).pin_memory() for m in cams]
-    h_out = torch.empty((B, C, W, W)).pin_memory()
-    h_bg = torch.empty((B, W, W), dtype=torch.bool).pin_memory()
+    # ---- e2e through the reference-facing wrapper with host buffers ----
+    bm = BaseModel(model, opt)
+    pin = lambda t: t.pin_memory()
+    pinned = {"images": [pin(t) for t in host_batch["images"]],
+              "cameras": [{k: pin(v) for k, v in c.items()} for c in host_batch["cameras"]]}
+    h_out = torch.empty((B, 3, W, W)).pin_memory()
+    model_kw = dict(noise=noise, uniforms=uniforms)
 
     def step_e2e():
-        dd = h_depth.to(devs, non_blocking=True)
-        ff = h_feat.to(devs, non_blocking=True)
-        cc = [m.to(devs, non_blocking=True) for m in h_cams]
-        gen_fs, bg = pm.forward_justpts(ff, dd, *cc)
-        h_out.copy_(gen_fs, non_blocking=True)
-        h_bg.copy_(bg, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+        _, out = model.forward(pinned, **model_kw)       # process_batch copies H2D (non_blocking from pinned memory)
+        img = 0.5 * out["PredImg"] + 0.5                  # BaseModel's rescale (base_model.py:96-99)
+        h_out.copy_(img, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup))
-    h2d = h_depth.numel() * 4 + h_feat.numel() * 4 + sum(m.numel() * 4 for m in h_cams)
-    d2h = h_out.numel() * 4 + h_bg.numel()
+    h2d = sum(t.numel() * 4 for t in pinned["images"]) + sum(v.numel() * 4 for c in pinned["cameras"] for v in c.values())
+    d2h = h_out.numel() * 4
 
-    # ---- roofline: the dominant kernel alone (ps_splat_points on pre-projected points), CUDA events ----
-    pts, _ = torch.ops.pixelsynth_b200.project_pts(d_depth, d_mats, W, 1e-2, False)
-    f3 = d_feat.reshape(B, C, -1)
-
-    def step_points():
-        return torch.ops.pixelsynth_b200.splat_points(pts, f3, W, K_PP, RADIUS, 1.0, 2, 0, 13, True, False)
-
-    for _ in range(3):
-        step_maps()
+    # ---- per-kernel device time over the same step (CUDA events recorded by the library on the launching stream) ----
+    step_resident()
     torch.cuda.synchronize()
     _lib.kernel_time_ms(None)
-    L.ps_timing_enable(1)  # CUDA events around fine_kernel on the launching stream, same step as `value`
+    L.ps_timing_enable(1)
     for _ in range(args.steps):
-        step_maps()
+        step_resident()
     torch.cuda.synchronize()
     L.ps_timing_enable(0)
-    kt_total, kt_n = _lib.kernel_time_ms("fine_kernel")
+    kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "conv_igemm_kernel", "lmconv_sample_kernel")}
     _lib.kernel_time_ms(None)
-    ms_points, _ = timed(step_points, args.steps, 3)
-    peak, peak_src = measured_peak()
-    kt = kt_total / max(kt_n, 1)
-    kernel_name = "fine_kernel"
-    achieved = BYTES_PER_VIEW_MAPS * B / (kt * 1e-3) / 1e9
+    last = model.last
+    cells_processed = int(model.outpaint2.steps_needed(last["order"], last["sample_mask"]).sum())
+    cells_sampled = int(last["sample_mask"].sum())
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    hbm_peak, tf_peak, peak_src = peaks()
+    step_ms = ms_res / args.steps
+    per_step = {n: (v[0] / args.steps, v[1] // args.steps) for n, v in kt.items()}
+    conv_flops = B * (FLOP_DECODER + FLOP_UNET + FLOP_VQ_ENC + FLOP_VQ_DEC)
+    rl = {
+        "splat fine_kernel": {"bound": "hbm", "achieved": BYTES_PER_VIEW_SPLAT_FUSED * B / (per_step["fine_kernel"][0] * 1e-3) / 1e9,
+                              "peak": hbm_peak, "unit": "GB/s", "ms_per_step": per_step["fine_kernel"][0],
+                              "note": "maps suppressed inside the pipeline (1.90 MB/view: compute bound); the map-emitting "
+                                      "mode (69.0 MB/view) reaches 0.455 of HBM peak, DESIGN.md section 4"},
+        "lmconv_sample_kernel": {"bound": "tensor", "achieved": FLOP_PER_CELL * cells_processed / (per_step["lmconv_sample_kernel"][0] * 1e-3) / 1e12,
+                                 "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["lmconv_sample_kernel"][0],
+                                 "cells_processed_per_step": cells_processed, "cells_sampled_per_step": cells_sampled},
+        "conv_igemm_kernel": {"bound": "tensor", "achieved": conv_flops / (per_step["conv_igemm_kernel"][0] * 1e-3) / 1e12,
+                              "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["conv_igemm_kernel"][0],
+                              "launches_per_step": per_step["conv_igemm_kernel"][1]},
+    }
+    for v in rl.values():
+        v["frac"] = v["achieved"] / v["peak"]
+        v["share_of_step"] = v["ms_per_step"] / step_ms
+    dom = max(rl, key=lambda k: rl[k]["ms_per_step"])
+    roof = dict(rl[dom])
+    roof.update({"kernel": dom, "traffic": None, "peak_source": peak_src})
     views_per_step = B * world
-    value = views_per_step * args.steps / (ms_maps * 1e-3)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_maps / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "metric": METRIC, "value": views_per_step * args.steps / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": views_per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "api": "PtsManipulator.forward_justpts (maps suppressed)"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": kernel_name, "ms_per_launch": kt, "share_of_step": kt / (ms_maps / args.steps),
-                     "rasterise_call_ms": ms_points / args.steps,
-                     "algorithmic_bytes_per_launch": BYTES_PER_VIEW_MAPS * B, "peak_source": peak_src},
-        "splat_hbm_gbs_whole_step": BYTES_PER_VIEW_MAPS * views_per_step * args.steps / (ms_maps * 1e-3) / 1e9 / world,
-        "splat_fused_views_per_s": views_per_step * args.steps / (ms_fused * 1e-3),
+                "d2h_bytes_per_step": d2h, "api": "ZbufferModelPts.forward + BaseModel rescale, host pinned in/out"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rl,
+        "lmconv_tokens_per_s": cells_sampled * world / (per_step["lmconv_sample_kernel"][0] * 1e-3),
+        "lmconv_cells_per_s": cells_processed * world / (per_step["lmconv_sample_kernel"][0] * 1e-3),
         "broadcast_ms": bcast_ms,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, dt = cpu_oracle_views_per_s(args.cpu_sample, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "%d views of the same workload (256x256, K=128) through oracle/splat_oracle.c, "
-                                          "single thread, %.1f s" % (args.cpu_sample, dt)}
+        s, st, n_sampled = cpu_oracle_view_seconds(args.cpu_tokens, 1)
+        line["cpu_baseline"] = {"value": 1.0 / s, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "1 view through the CPU oracle, one thread; sampler timed reference-style on %d tokens "
+                                          "(%.3f s/token) and extrapolated to the view's %d sampled cells" %
+                                          (args.cpu_tokens, st["lmconv_per_token"], n_sampled),
+                                "stage_seconds": st}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -19,7 +19,7 @@
 
 namespace ps {
 
-constexpr int LM_THREADS = 256;
+constexpr int LM_THREADS = 1024;  // many k-groups: the column GEMVs are L2-latency bound, so rows per thread must be few
 constexpr int LM_G = 32;          // grid side
 constexpr int LM_CELLS = LM_G * LM_G;
 constexpr int LM_F = 80;          // nr_filters
@@ -53,11 +53,11 @@ struct LmParams {
 
 struct LmSmem {
   float xin[9 * 2 * LM_F];
-  float partial[2048];
+  float partial[8192];
   float res[LM_CLASSES];
   float og[LM_F], mid[LM_F];
   int taps[3][9], nbr[3][9], nact[3];
-  float red[LM_THREADS / 32];
+  float red[32];
   float bcast[2];
   int token;
 };
@@ -84,12 +84,12 @@ __device__ __forceinline__ void gemv(const LmParams& p, LmSmem& sm, int w_off, i
       const __nv_bfloat16* wr = wbase + (size_t)(taps[ti] * cin + ci) * COUT;
       const float* xr = sm.xin + k;
       int j = 0;
-      for (; j + 4 <= run; j += 4) {
-        uint4 w[4];
+      for (; j + 8 <= run; j += 8) {
+        uint4 w[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(wr + (size_t)(j + u) * COUT));
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(wr + (size_t)(j + u) * COUT));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const float x = xr[j + u];
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w[u]);
 #pragma unroll
@@ -122,11 +122,15 @@ __device__ __forceinline__ void gemv(const LmParams& p, LmSmem& sm, int w_off, i
     for (int e = 0; e < 8; ++e) sm.partial[g * COUT + cq * 8 + e] = acc[e];
   }
   __syncthreads();
-  for (int co = tid; co < COUT; co += LM_THREADS) {
-    float s = p.bias[b_off + co];
-#pragma unroll 5
-    for (int gg = 0; gg < NG; ++gg) s += sm.partial[gg * COUT + co];
-    sm.res[co] = s;
+  {  // R threads per output channel sum the k-group partials, then a shuffle tree
+    constexpr int R = COUT <= 128 ? 8 : (COUT <= 256 ? 4 : 2);
+    const int co = tid / R, part = tid - co * R;
+    float s = 0.f;
+    if (co < COUT)
+      for (int gg = part; gg < NG; gg += R) s += sm.partial[gg * COUT + co];
+#pragma unroll
+    for (int off = R / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (co < COUT && part == 0) sm.res[co] = s + p.bias[b_off + co];
   }
   __syncthreads();
 }
@@ -276,40 +280,44 @@ __global__ void __launch_bounds__(LM_THREADS) lmconv_sample_kernel(const LmParam
     if (do_sample) {
       // token = first j with cumsum(softmax(logits / T))_j > u
       const int lane = tid & 31, warp = tid >> 5;
-      const float l0 = sm.res[2 * tid] * p.inv_temperature, l1 = sm.res[2 * tid + 1] * p.inv_temperature;
+      const bool act = tid < LM_CLASSES / 2;  // 256 threads own two logits each
+      const float l0 = act ? sm.res[2 * tid] * p.inv_temperature : -INFINITY;
+      const float l1 = act ? sm.res[2 * tid + 1] * p.inv_temperature : -INFINITY;
       float mx = fmaxf(l0, l1);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-      if (lane == 0) sm.red[warp] = mx;
+      if (lane == 0 && warp < 8) sm.red[warp] = mx;
       __syncthreads();
       if (tid == 0) {
         float m = sm.red[0];
-        for (int w = 1; w < LM_THREADS / 32; ++w) m = fmaxf(m, sm.red[w]);
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, sm.red[w]);
         sm.bcast[0] = m;
         sm.token = LM_CLASSES - 1;
       }
       __syncthreads();
       mx = sm.bcast[0];
-      const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx);
+      const float e0 = act ? __expf(l0 - mx) : 0.f, e1 = act ? __expf(l1 - mx) : 0.f;
       float incl = e0 + e1;  // inclusive scan of the per-thread pair sums
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const float v = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += v;
       }
-      if (lane == 31) sm.red[warp] = incl;
+      if (lane == 31 && warp < 8) sm.red[warp] = incl;
       __syncthreads();
       float base = 0.f, total = 0.f;
-      for (int w = 0; w < LM_THREADS / 32; ++w) {
+      for (int w = 0; w < 8; ++w) {
         if (w < warp) base += sm.red[w];
         total += sm.red[w];
       }
       const float thr = p.uniforms[(size_t)b * p.ustride + drawn] * total;
       const float c0 = base + incl - e1, c1 = base + incl;
-      if (c0 > thr)
-        atomicMin(&sm.token, 2 * tid);
-      else if (c1 > thr)
-        atomicMin(&sm.token, 2 * tid + 1);
+      if (act) {
+        if (c0 > thr)
+          atomicMin(&sm.token, 2 * tid);
+        else if (c1 > thr)
+          atomicMin(&sm.token, 2 * tid + 1);
+      }
       __syncthreads();
       if (tid == 0) codes[pos] = sm.token;
       ++drawn;

@@ -328,10 +328,11 @@ def main():
         step_resident()
     torch.cuda.synchronize()
     L.ps_timing_enable(0)
-    kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "conv_igemm_kernel", "lmconv_sample_kernel")}
+    kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "conv_igemm_kernel", "lmconv_tc_kernel")}
     _lib.kernel_time_ms(None)
     last = model.last
-    cells_processed = int(model.outpaint2.steps_needed(last["order"], last["sample_mask"]).sum())
+    cells_processed = int(model.outpaint2.last_levels[-1])   # rows the sampler pushed through the network this step
+    levels = len(model.outpaint2.last_levels) - 1
     cells_sampled = int(last["sample_mask"].sum())
 
     if rank != 0:
@@ -348,9 +349,10 @@ def main():
                               "peak": hbm_peak, "unit": "GB/s", "ms_per_step": per_step["fine_kernel"][0],
                               "note": "maps suppressed inside the pipeline (1.90 MB/view: compute bound); the map-emitting "
                                       "mode (69.0 MB/view) reaches 0.455 of HBM peak, DESIGN.md section 4"},
-        "lmconv_sample_kernel": {"bound": "tensor", "achieved": FLOP_PER_CELL * cells_processed / (per_step["lmconv_sample_kernel"][0] * 1e-3) / 1e12,
-                                 "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["lmconv_sample_kernel"][0],
-                                 "cells_processed_per_step": cells_processed, "cells_sampled_per_step": cells_sampled},
+        "lmconv_tc_kernel": {"bound": "tensor", "achieved": FLOP_PER_CELL * cells_processed / (per_step["lmconv_tc_kernel"][0] * 1e-3) / 1e12,
+                                 "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["lmconv_tc_kernel"][0],
+                                 "cells_processed_per_step": cells_processed, "cells_sampled_per_step": cells_sampled,
+                                 "dependency_levels": levels},
         "conv_igemm_kernel": {"bound": "tensor", "achieved": conv_flops / (per_step["conv_igemm_kernel"][0] * 1e-3) / 1e12,
                               "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["conv_igemm_kernel"][0],
                               "launches_per_step": per_step["conv_igemm_kernel"][1]},
@@ -369,8 +371,8 @@ def main():
         "e2e": {"value": views_per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "ZbufferModelPts.forward + BaseModel rescale, host pinned in/out"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rl,
-        "lmconv_tokens_per_s": cells_sampled * world / (per_step["lmconv_sample_kernel"][0] * 1e-3),
-        "lmconv_cells_per_s": cells_processed * world / (per_step["lmconv_sample_kernel"][0] * 1e-3),
+        "lmconv_tokens_per_s": cells_sampled * world / (per_step["lmconv_tc_kernel"][0] * 1e-3),
+        "lmconv_cells_per_s": cells_processed * world / (per_step["lmconv_tc_kernel"][0] * 1e-3),
         "broadcast_ms": bcast_ms,
     }
     if world == 1 and not args.no_cpu_baseline:

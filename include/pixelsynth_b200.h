@@ -192,20 +192,33 @@ int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, int* dist_hos
                         uint16_t* words_host, uint8_t* sample_mask_host);
 
 /* ------------------------------------------------------------------------------------------------
- * Activation-cached autoregressive sampler of the locally-masked-convolution PixelCNN (csrc/lmconv.cu).
+ * Wavefront tensor-core sampler of the locally-masked-convolution PixelCNN (csrc/lmconv_tc.cu).
  * Replaces models/lmconv/sample.py:8-73 (sample) + models/lmconv/model.py:110-155 (OurPixelCNN.forward, called
- * once per token there).  Weights: one bf16 array holding every layer as [tap][cin][cout] (masked 3x3 convs; nin
- * layers are a single tap with the weight-norm g*v/|v| already applied) and one fp32 bias array; offsets below are
- * element offsets into them.  ops lists the 18 column operations after u_init in execution order (14 gated
- * resnets, kind 0; 4 dilated convs + PONO, kind 1) with the ids (0..32) of the cached tensors they read / write.
- *   order (B,1024) i32, words (B,3,1024) u16, sample_mask (B,1024) u8: as produced by ps_lmconv_glue_host
- *   codes (B,1024) i64: in = known codes, out = sampled cells filled (sample != 0)
- *   uniforms (B,stride) f32: the k-th sampled cell of image b takes the first class whose cumulative
- *            softmax(logits/temperature) exceeds uniforms[b][k]
- *   nsteps (B) i32: cells of the generation order to process (everything after the last sampled cell is skipped)
- *   logits_out (B,1024,512) f32 or NULL: logits of every processed cell (teacher-forced parity surface)
- *   cache: ps_lmconv_cache_bytes(B) bytes of device scratch (the activation cache)
+ * once per token there).  The masks make the network causal in generation order, so every cell's activation
+ * column is computed once; cells that are not masked-in neighbours of each other are independent, so the
+ * dependency DAG is levelled (ps_lmconv_levels_host) and each level is one launch over (image, cell) rows.
+ *
+ * ps_lmconv_plan: the network as the kernel consumes it (built by pixelsynth_b200/lmconv.py from the reference's
+ * state dict):
+ *   wblob   fp16 weight tiles, one per K chunk: [w_rows output channels][64 k] K-major in the 128-byte-swizzle
+ *           shared-memory image tcgen05 reads (chunk 16B-group j of row r stored at group j ^ (r & 7))
+ *   chunks  the static K-chunk schedule.  a_kind 0: rows gathered from cached tensor a_tensor through mask
+ *           `mask` (0 = A dil 1, 1 = B dil 1, 2 = B dil 2), K = (non-centre tap slot, channel), chunk kc of it,
+ *           channels start at ch_off8*8 of the 240-wide cache row; a_kind 1: the row's own cell of a_tensor
+ *           (nin_skip); a_kind 2: written by the epilogue of the previous GEMM (the centre tap).
+ *           d_col = TMEM column of the accumulator, flags bit0 = accumulate, bit1 = last chunk of the GEMM,
+ *           bits 2-3 = which accumulator barrier that completes (0/1 ping-pong, 2 = logits), bit4 = the stages of
+ *           GEMM (bit5 parity)'s centre chunks are free once this chunk has been multiplied (it is the chunk
+ *           PS_LMCONV_STAGES before the last centre chunk of that GEMM)
+ *   epi_first[g]  index of the first a_kind-2 chunk of GEMM g (GEMMs in execution order; nin_out = 4 quarters)
+ *   ops     the 18 column operations after u_init (14 gated resnets, kind 0; 4 dilated convs + PONO, kind 1) with
+ *           the ids (0..32) of the cached tensors they write (mid, out) and their bias offsets
+ * ps_lmconv_row: bc = image << 10 | cell; w01 = mask word A | mask word B << 16; w2_flags = mask word B-dil-2 |
+ *           bit16 sampled | bit17 logits wanted | bit18 valid; uidx = index of the row's uniform number
  * ------------------------------------------------------------------------------------------------ */
+#define PS_LMCONV_MAX_GEMMS 40
+#define PS_LMCONV_STAGES 6
+
 typedef struct {
   int kind;
   int og, a, mid, out;
@@ -213,20 +226,49 @@ typedef struct {
 } ps_lmconv_op;
 
 typedef struct {
-  const void* weights; /* bf16 */
-  const float* bias;
-  int w_uinit, b_uinit, w_nin, b_nin;
+  uint32_t w_off16;
+  uint16_t w_rows;
+  uint8_t a_kind, a_tensor, mask, cin8, kc, ch_off8;
+  uint16_t d_col;
+  uint8_t flags, pad;
+} ps_lmconv_chunk;
+
+typedef struct {
+  int32_t bc;
+  uint32_t w01;
+  uint32_t w2_flags;
+  int32_t uidx;
+} ps_lmconv_row;
+
+typedef struct {
+  const void* wblob;             /* device */
+  const ps_lmconv_chunk* chunks; /* device */
+  int n_chunks_body, n_chunks_total; /* without / with the nin_out quarters */
+  int epi_first[PS_LMCONV_MAX_GEMMS];
+  const void* w_uinit; /* device fp16 [9 taps][513][80] */
+  const float* bias;   /* device */
+  int b_uinit, b_nin;
   ps_lmconv_op ops[18];
-} ps_lmconv_weights;
+} ps_lmconv_plan;
 
-size_t ps_lmconv_cache_bytes(int B);
-int ps_lmconv_sample(const ps_lmconv_weights* w, int B, const int* order, const uint16_t* words,
-                     const uint8_t* sample_mask, long long* codes, const float* uniforms, int uniforms_stride,
-                     float temperature, const int* nsteps, int sample, float* logits_out, void* cache,
-                     size_t cache_bytes, void* stream);
+size_t ps_lmconv_tc_cache_bytes(int B);
 
-/* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels (currently
- * "fine_kernel") are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
+/* Host: rows of every dependency level, level by level (rows_out holds up to B*1024 rows, level_offsets
+ * max_levels + 1 ints).  mode 0 = sampling (order (B,1024) i32, words (B,3,1024) u16, sample_mask (B,1024) u8 as
+ * produced by ps_lmconv_glue_host; cells after an image's last sampled cell are skipped, images with nothing to
+ * sample produce no rows); mode 1 = teacher-forced logits of all cells (one level, sample_mask may be NULL). */
+int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t* sample_mask, int B, int mode,
+                          ps_lmconv_row* rows_out, int* level_offsets, int max_levels, int* n_levels);
+
+/* Device: runs the levels in order on `stream`.  codes (B,1024) i64: in = known codes, out = sampled cells filled;
+ * uniforms (B,stride) f32: the k-th sampled cell (in generation order) of image b takes the first class whose
+ * cumulative softmax(logits/temperature) exceeds uniforms[b][k]; logits_out (B,1024,512) f32 or NULL receives the
+ * logits of rows flagged bit17; cache: ps_lmconv_tc_cache_bytes(B) bytes of device scratch. */
+int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* rows_dev, const int* level_offsets_host,
+                     int n_levels, long long* codes, const float* uniforms, int uniforms_stride, float temperature,
+                     float* logits_out, void* cache, size_t cache_bytes, void* stream);
+
+/* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels  are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;
  * ps_timing_collect(NULL, ...) returns the sum over all names and releases the events. */
 void ps_timing_enable(int on);

@@ -121,33 +121,42 @@ def _nin(sd, p, x):
     return torch.einsum("oc,bchw->bohw", w, x) + sd[p + "lin_a.bias"][None, :, None, None]
 
 
-def _resnet(sd, p, og, a, mask):
+def _resnet(sd, p, og, a, mask, trace=None):
     x = _masked_conv(_celu(og), mask, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1)
     x = _pono(x)
     if a is not None:
         x = x + _nin(sd, p + "nin_skip.", _celu(a))
+    if trace is not None:
+        trace.append(x)
     y = _masked_conv(_celu(x), mask, sd[p + "conv_out.weight"], sd[p + "conv_out.bias"], 1)
     ya, yb = torch.chunk(y, 2, dim=1)
     return og + _pono(ya) * torch.sigmoid(yb)
 
 
-def lmconv_logits(sd, data, m_init, m_undil, m_dil):
-    """data (B,512,32,32) one-hot (zeros at not-yet-generated cells); masks (B,9,1024) float -> logits (B,512,32,32)."""
+def lmconv_logits(sd, data, m_init, m_undil, m_dil, trace=None):
+    """data (B,512,32,32) one-hot (zeros at not-yet-generated cells); masks (B,9,1024) float -> logits (B,512,32,32).
+    trace (a list) receives every intermediate tensor in execution order: u_init's output, then per gated resnet its
+    mid and output tensors, per dilated conv its output."""
+    def keep(t):
+        if trace is not None:
+            trace.append(t)
+        return t
+
     x = torch.cat((data, torch.ones_like(data[:, :1])), 1)
-    u_list = [_pono(_masked_conv(x, m_init, sd["u_init.weight"], sd["u_init.bias"], 1))]
+    u_list = [keep(_pono(_masked_conv(x, m_init, sd["u_init.weight"], sd["u_init.bias"], 1)))]
     for i in range(2):
         for j in range(2):
-            u_list.append(_resnet(sd, f"up_layers.{i}.u_stream.{j}.", u_list[-1], None, m_undil))
-        u_list.append(_pono(_masked_conv(u_list[-1], m_dil, sd[f"downsize_u_stream.{i}.weight"],
-                                         sd[f"downsize_u_stream.{i}.bias"], 2)))
+            u_list.append(keep(_resnet(sd, f"up_layers.{i}.u_stream.{j}.", u_list[-1], None, m_undil, trace)))
+        u_list.append(keep(_pono(_masked_conv(u_list[-1], m_dil, sd[f"downsize_u_stream.{i}.weight"],
+                                              sd[f"downsize_u_stream.{i}.bias"], 2))))
     for j in range(2):
-        u_list.append(_resnet(sd, f"up_layers.2.u_stream.{j}.", u_list[-1], None, m_undil))
+        u_list.append(keep(_resnet(sd, f"up_layers.2.u_stream.{j}.", u_list[-1], None, m_undil, trace)))
     u = u_list.pop()
     for i, n in enumerate((2, 3, 3)):
         for j in range(n):
-            u = _resnet(sd, f"down_layers.{i}.u_stream.{j}.", u, u_list.pop(), m_undil)
+            u = keep(_resnet(sd, f"down_layers.{i}.u_stream.{j}.", u, u_list.pop(), m_undil, trace))
         if i < 2:
-            u = _pono(_masked_conv(u, m_dil, sd[f"upsize_u_stream.{i}.weight"], sd[f"upsize_u_stream.{i}.bias"], 2))
+            u = keep(_pono(_masked_conv(u, m_dil, sd[f"upsize_u_stream.{i}.weight"], sd[f"upsize_u_stream.{i}.bias"], 2)))
     return _nin(sd, "nin_out.", F.elu(u))
 
 

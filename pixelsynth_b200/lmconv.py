@@ -1,7 +1,9 @@
-"""Host side of the activation-cached lmconv sampler (csrc/lmconv.cu) and of the native order/mask glue (csrc/glue.cu).
+"""Host side of the wavefront tensor-core lmconv sampler (csrc/lmconv_tc.cu) and of the native order/mask glue
+(csrc/glue.cu).
 
 LmconvB200 takes the reference's OurPixelCNN state dict (models/lmconv/model.py:61-108, instantiated as at
-models/z_buffermodel.py:62-74), packs every layer as [tap][cin][cout] bf16 and exposes
+models/z_buffermodel.py:62-74), packs every layer as the kernel's K-chunk schedule of pre-swizzled fp16 weight tiles
+(ps_lmconv_plan, include/pixelsynth_b200.h) and exposes
   sample(codes, order, words, sample_mask, uniforms, temperature)   ~ models/lmconv/sample.py:8-73
   logits(codes, order, words)                                        ~ OurPixelCNN.forward (teacher forced)
 """
@@ -14,6 +16,10 @@ from . import _lib
 from ._lib import check
 
 U0, DS0, DS1, US0, US1 = 0, 13, 14, 31, 32
+MAX_GEMMS = 40
+MAX_LEVELS = 1025
+STAGES = 6  # PS_LMCONV_STAGES
+A_GATHER, A_CENTRE, A_EPILOGUE = 0, 1, 2
 
 
 class _Op(ctypes.Structure):
@@ -21,9 +27,41 @@ class _Op(ctypes.Structure):
                                             "b_out")]
 
 
-class _Weights(ctypes.Structure):
-    _fields_ = [("weights", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("w_uinit", ctypes.c_int),
-                ("b_uinit", ctypes.c_int), ("w_nin", ctypes.c_int), ("b_nin", ctypes.c_int), ("ops", _Op * 18)]
+class _Chunk(ctypes.Structure):
+    _fields_ = [("w_off16", ctypes.c_uint32), ("w_rows", ctypes.c_uint16), ("a_kind", ctypes.c_uint8),
+                ("a_tensor", ctypes.c_uint8), ("mask", ctypes.c_uint8), ("cin8", ctypes.c_uint8), ("kc", ctypes.c_uint8),
+                ("ch_off8", ctypes.c_uint8), ("d_col", ctypes.c_uint16), ("flags", ctypes.c_uint8), ("pad", ctypes.c_uint8)]
+
+
+class _Row(ctypes.Structure):
+    _fields_ = [("bc", ctypes.c_int32), ("w01", ctypes.c_uint32), ("w2_flags", ctypes.c_uint32), ("uidx", ctypes.c_int32)]
+
+
+class _Plan(ctypes.Structure):
+    _fields_ = [("wblob", ctypes.c_void_p), ("chunks", ctypes.c_void_p), ("n_chunks_body", ctypes.c_int),
+                ("n_chunks_total", ctypes.c_int), ("epi_first", ctypes.c_int * MAX_GEMMS), ("w_uinit", ctypes.c_void_p),
+                ("bias", ctypes.c_void_p), ("b_uinit", ctypes.c_int), ("b_nin", ctypes.c_int), ("ops", _Op * 18)]
+
+
+assert ctypes.sizeof(_Chunk) == 16 and ctypes.sizeof(_Row) == 16
+
+NONCENTRE_TAPS = [0, 1, 2, 3, 5, 6, 7, 8]
+
+
+def swizzle_tiles(mat):
+    """(rows, K) fp32 with rows % 8 == 0 and K % 64 == 0 -> list of K/64 uint8 arrays, each the fp16 [rows][64] K-major
+    tile in the 128-byte-swizzle image tcgen05 reads: 16-byte group j of row r is stored at group j ^ (r & 7)."""
+    rows, K = mat.shape
+    assert rows % 8 == 0 and K % 64 == 0
+    bits = mat.to(torch.float16).contiguous().view(torch.int16).numpy().reshape(rows, K // 64, 8, 8)
+    src = np.arange(8)[None, :] ^ (np.arange(rows)[:, None] & 7)          # stored group j holds logical group j ^ (r & 7)
+    out = np.take_along_axis(bits, src[:, None, :, None], axis=2)          # (rows, K/64, 8, 8)
+    return [np.ascontiguousarray(out[:, kc]).view(np.uint8).reshape(-1) for kc in range(K // 64)]
+
+
+def _pad_k(mat, mult=64):
+    pad = (-mat.shape[1]) % mult
+    return mat if pad == 0 else torch.cat([mat, torch.zeros(mat.shape[0], pad)], 1)
 
 
 def glue_host(background_mask):
@@ -44,16 +82,8 @@ def glue_host(background_mask):
 class LmconvB200:
     def __init__(self, sd, device="cuda"):
         self.device = device
-        ws, bs = [], []
-        self._wn = self._bn = 0
-
-        def add_w(t):  # t: (rows, cout) fp32
-            off = self._wn
-            flat = t.reshape(-1).float()
-            pad = (-flat.numel()) % 8          # keep every block 16-byte aligned for the kernel's uint4 loads
-            ws.append(torch.cat([flat, torch.zeros(pad)]))
-            self._wn += flat.numel() + pad
-            return off
+        blobs, chunks, bs, epi_first = [], [], [], []
+        self._woff = self._bn = 0
 
         def add_b(t):
             off = self._bn
@@ -61,32 +91,64 @@ class LmconvB200:
             self._bn += t.numel()
             return off
 
-        def conv(prefix):  # (Cout,Cin,3,3) -> [tap][cin][cout]
+        def add_chunks(tiles, rows, a_kind, tensor, mask, cin8, ch_off8, d_col, first_acc, last_bar=None):
+            """one chunk per tile; accumulate flag off only for the very first chunk when first_acc is False"""
+            for kc, tile in enumerate(tiles):
+                c = _Chunk()
+                c.w_off16, c.w_rows, c.a_kind, c.a_tensor, c.mask, c.cin8 = self._woff // 16, rows, a_kind, tensor, mask, cin8
+                c.kc, c.ch_off8, c.d_col = kc, ch_off8, d_col
+                c.flags = 1 if (first_acc or kc > 0) else 0
+                if last_bar is not None and kc == len(tiles) - 1:
+                    c.flags |= 2 | (last_bar << 2)
+                chunks.append(c)
+                blobs.append(tile)
+                self._woff += tile.size
+
+        def conv_mats(prefix):  # (Cout,Cin,3,3) -> non-centre (Cout, 8*Cin) in tap-slot order, centre (Cout, Cin)
             w = sd[prefix + "weight"].float()
-            return add_w(w.permute(2, 3, 1, 0).reshape(9 * w.shape[1], w.shape[0])), add_b(sd[prefix + "bias"])
+            cout, cin = w.shape[:2]
+            w9 = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+            return w9[:, NONCENTRE_TAPS].reshape(cout, 8 * cin), w9[:, 4], add_b(sd[prefix + "bias"])
 
-        def nin(prefix):   # weight-normed Linear: g * v / |v| per output row -> [cin][cout]
+        def nin_mat(prefix):   # weight-normed Linear: g * v / |v| per output row -> (Cout, Cin)
             v = sd[prefix + "lin_a.weight_v"].float()
-            w = sd[prefix + "lin_a.weight_g"].float() * v / v.norm(dim=1, keepdim=True)
-            return add_w(w.t().contiguous()), add_b(sd[prefix + "lin_a.bias"])
+            return sd[prefix + "lin_a.weight_g"].float() * v / v.norm(dim=1, keepdim=True), add_b(sd[prefix + "lin_a.bias"])
 
-        self.w = _Weights()
-        self.w.w_uinit, self.w.b_uinit = conv("u_init.")
+        self.gemm = 0
+
+        def masked_gemm(prefix, src, mask, raw, skip=None):
+            """chunks of one masked 3x3 conv reading cached tensor `src`: gathered non-centre taps, [nin_skip of tensor
+            skip[0] into the next 80 accumulator columns,] then the centre tap written by the previous epilogue"""
+            wn, wc, b = conv_mats(prefix)
+            cout, cin = wc.shape
+            col = (self.gemm & 1) * 160
+            add_chunks(swizzle_tiles(wn), cout, A_GATHER, src, mask, cin // 8, 20 if raw else 0, col, False)
+            bskip = -1
+            if skip is not None:
+                ws, bskip = nin_mat(skip[1])
+                add_chunks(swizzle_tiles(_pad_k(ws)), 80, A_CENTRE, skip[0], 0, 20, 0, col + 80, False)
+            epi_first.append(len(chunks))
+            add_chunks(swizzle_tiles(_pad_k(wc)), cout, A_EPILOGUE, src, mask, cin // 8, 0, col, True, last_bar=self.gemm & 1)
+            self.gemm += 1
+            return b, bskip
+
+        w = sd["u_init.weight"].float()                       # (80, 513, 3, 3) -> [tap][cin][cout]
+        self.w_uinit = w.permute(2, 3, 1, 0).reshape(9, 513, 80).contiguous().to(device=device, dtype=torch.float16)
+        self.plan = _Plan()
+        self.plan.b_uinit = add_b(sd["u_init.bias"])
         ops = []
 
         def resnet(prefix, og, a, mid, out):
             o = _Op()
             o.kind, o.og, o.a, o.mid, o.out = 0, og, a, mid, out
-            o.w_in, o.b_in = conv(prefix + "conv_input.")
-            if a >= 0:
-                o.w_skip, o.b_skip = nin(prefix + "nin_skip.")
-            o.w_out, o.b_out = conv(prefix + "conv_out.")
+            o.b_in, o.b_skip = masked_gemm(prefix + "conv_input.", og, 1, False, None if a < 0 else (a, prefix + "nin_skip."))
+            o.b_out, _ = masked_gemm(prefix + "conv_out.", mid, 1, False)
             ops.append(o)
 
         def dilated(prefix, src, dst):
             o = _Op()
             o.kind, o.og, o.a, o.mid, o.out = 1, src, -1, -1, dst
-            o.w_in, o.b_in = conv(prefix)
+            o.b_in, _ = masked_gemm(prefix, src, 2, True)
             ops.append(o)
 
         # up pass (model.py:130-141); u_list = [U0, 2, 4, DS0, 6, 8, DS1, 10, 12]
@@ -109,59 +171,85 @@ class LmconvB200:
         resnet("down_layers.2.u_stream.0.", US1, 4, 25, 26)
         resnet("down_layers.2.u_stream.1.", 26, 2, 27, 28)
         resnet("down_layers.2.u_stream.2.", 28, U0, 29, 30)
-        assert len(ops) == 18
+        assert len(ops) == 18 and self.gemm == 32
         for i, o in enumerate(ops):
-            self.w.ops[i] = o
-        self.w.w_nin, self.w.b_nin = nin("nin_out.")
-        self.W = torch.cat(ws).to(device=device, dtype=torch.bfloat16).contiguous()
+            self.plan.ops[i] = o
+        self.plan.n_chunks_body = len(chunks)
+        wno, self.plan.b_nin = nin_mat("nin_out.")            # (512, 80): four 128-class quarters, K padded to 128
+        for q in range(4):
+            epi_first.append(len(chunks))
+            add_chunks(swizzle_tiles(_pad_k(wno[128 * q:128 * q + 128])), 128, A_EPILOGUE, 30, 0, 10, 0, 128 * q, False,
+                       last_bar=2 if q == 3 else None)
+        self.plan.n_chunks_total = len(chunks)
+        assert len(epi_first) <= MAX_GEMMS
+        for i, v in enumerate(epi_first):
+            self.plan.epi_first[i] = v
+        # Centre-stage release points (chunk flag bit 4, bit 5 = barrier parity): the stages of GEMM i's centre chunks
+        # are free once the chunk STAGES before the last of them has been multiplied.  nin_out quarters 0-2 reuse
+        # stages of body chunks that completed with the last GEMM; quarter 3 waits for quarter 0 (as "GEMM 33").
+        n_centre = [3 if chunks[v].cin8 == 20 else 2 for v in epi_first]
+        for i, v in enumerate(epi_first):
+            if i in (32, 33, 34):
+                continue
+            c = chunks[v + n_centre[i] - 1 - STAGES]
+            assert v + n_centre[i] - 1 - STAGES >= 0 and not (c.flags & 16)
+            c.flags |= 16 | (((33 if i == 35 else i) & 1) << 5)
+        self.wblob = torch.from_numpy(np.concatenate(blobs)).to(device)
+        self.chunks = torch.from_numpy(np.frombuffer(b"".join(bytes(c) for c in chunks), dtype=np.uint8).copy()).to(device)
         self.bias = torch.cat(bs).to(device).contiguous()
-        self.w.weights, self.w.bias = self.W.data_ptr(), self.bias.data_ptr()
+        self.plan.wblob, self.plan.chunks = self.wblob.data_ptr(), self.chunks.data_ptr()
+        self.plan.w_uinit, self.plan.bias = self.w_uinit.data_ptr(), self.bias.data_ptr()
         self._cache = None
-
-    def _run(self, codes, order, words, sample_mask, uniforms, temperature, nsteps, sample, want_logits):
-        dev = self.device
-        B = codes.shape[0]
-        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a).to(device=dev, dtype=dt).contiguous()
-        codes_d = t(codes, torch.int64).reshape(B, 1024).clone()
-        order_d = t(order, torch.int32).reshape(B, 1024)
-        wn = words.detach().cpu().numpy() if torch.is_tensor(words) else np.asarray(words)
-        words_d = torch.from_numpy(np.ascontiguousarray(wn).astype(np.uint16).view(np.int16).reshape(B, 3, 1024)).to(dev)
-        smask_d = t(sample_mask, torch.uint8).reshape(B, 1024)
-        nsteps_d = t(nsteps, torch.int32).reshape(B)
-        uni_d = None if uniforms is None else t(uniforms, torch.float32).reshape(B, -1)
-        logits = torch.empty((B, 1024, 512), dtype=torch.float32, device=dev) if want_logits else None
-        nbytes = _lib.lib().ps_lmconv_cache_bytes(B)
-        if self._cache is None or self._cache.numel() < nbytes:
-            self._cache = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(self.W.device):
-            check(_lib.lib().ps_lmconv_sample(
-                ctypes.byref(self.w), B, order_d.data_ptr(), words_d.data_ptr(), smask_d.data_ptr(), codes_d.data_ptr(),
-                None if uni_d is None else uni_d.data_ptr(), 0 if uni_d is None else uni_d.shape[1], float(temperature),
-                nsteps_d.data_ptr(), int(sample), None if logits is None else logits.data_ptr(), self._cache.data_ptr(),
-                nbytes, torch.cuda.current_stream().cuda_stream), "ps_lmconv_sample")
-        return codes_d.view(B, 32, 32), logits
+        self.last_levels = None
 
     @staticmethod
-    def steps_needed(order, sample_mask):
-        """cells of the generation order up to and including the last sampled one (0 when nothing is sampled)."""
-        sm = np.asarray(sample_mask).reshape(len(order), -1)
-        out = np.zeros(len(order), np.int32)
-        for b in range(len(order)):
-            hit = np.nonzero(sm[b][np.asarray(order[b])])[0]
-            out[b] = hit[-1] + 1 if hit.size else 0
-        return out
+    def levels_host(order, words, sample_mask, mode):
+        """ps_lmconv_levels_host: -> (rows uint8 array of 16-byte records, level offsets list)."""
+        order = np.ascontiguousarray(np.asarray(order).reshape(-1, 1024).astype(np.int32))
+        B = order.shape[0]
+        words = np.ascontiguousarray(np.asarray(words).reshape(B, 3, 1024).astype(np.uint16))
+        sm = None if sample_mask is None else np.ascontiguousarray(np.asarray(sample_mask).reshape(B, 1024).astype(np.uint8))
+        rows = np.zeros((B * 1024, 16), np.uint8)
+        offs = np.zeros(MAX_LEVELS + 1, np.int32)
+        n = ctypes.c_int(0)
+        check(_lib.lib().ps_lmconv_levels_host(order.ctypes.data, words.ctypes.data, None if sm is None else sm.ctypes.data, B,
+                                               int(mode), rows.ctypes.data, offs.ctypes.data, MAX_LEVELS, ctypes.byref(n)),
+              "ps_lmconv_levels_host")
+        offs = offs[:n.value + 1].copy() if n.value else np.zeros(1, np.int32)
+        return rows[:int(offs[-1])], offs
+
+    def _run(self, codes, order, words, sample_mask, uniforms, temperature, mode):
+        dev = self.device
+        B = codes.shape[0]
+        wn = words.detach().cpu().numpy() if torch.is_tensor(words) else np.asarray(words)
+        ordn = order.detach().cpu().numpy() if torch.is_tensor(order) else np.asarray(order)
+        rows, offs = self.levels_host(ordn, wn, sample_mask, mode)
+        self.last_levels = offs
+        codes_d = torch.as_tensor(codes).to(device=dev, dtype=torch.int64).reshape(B, 1024).clone()
+        logits = torch.empty((B, 1024, 512), dtype=torch.float32, device=dev) if mode == 1 else None
+        if len(offs) > 1:
+            rows_d = torch.from_numpy(rows).to(dev)
+            uni_d = None if uniforms is None else torch.as_tensor(uniforms).to(device=dev, dtype=torch.float32).reshape(B, -1).contiguous()
+            nbytes = _lib.lib().ps_lmconv_tc_cache_bytes(B)
+            if self._cache is None or self._cache.numel() < nbytes:
+                self._cache = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(self.wblob.device):
+                check(_lib.lib().ps_lmconv_tc_run(
+                    ctypes.byref(self.plan), B, rows_d.data_ptr(), offs.ctypes.data, len(offs) - 1, codes_d.data_ptr(),
+                    None if uni_d is None else uni_d.data_ptr(), 0 if uni_d is None else uni_d.shape[1], float(temperature),
+                    None if logits is None else logits.data_ptr(), self._cache.data_ptr(), nbytes,
+                    torch.cuda.current_stream().cuda_stream), "ps_lmconv_tc_run")
+        return codes_d.view(B, 32, 32), logits
 
     def sample(self, codes, order, words, sample_mask, uniforms, temperature=1.0):
         """codes (B,32,32) int64 with the known cells; returns codes with the sample_mask cells drawn in generation
         order (the argmax of sample.py's one-hot `data`, as z_buffermodel.py:249 takes it)."""
         smn = sample_mask.detach().cpu().numpy() if torch.is_tensor(sample_mask) else np.asarray(sample_mask)
-        ordn = order.detach().cpu().numpy() if torch.is_tensor(order) else np.asarray(order)
-        nsteps = self.steps_needed(ordn, smn)
-        out, _ = self._run(codes, order, words, smn.astype(np.uint8), uniforms, temperature, nsteps, 1, False)
+        out, _ = self._run(codes, order, words, smn.astype(np.uint8), uniforms, temperature, 0)
         return out
 
     def logits(self, codes, order, words):
         """Teacher-forced logits of every cell given all codes: (B,512,32,32) like OurPixelCNN.forward."""
         B = codes.shape[0]
-        _, lg = self._run(codes, order, words, np.zeros((B, 1024), np.uint8), None, 1.0, np.full(B, 1024, np.int32), 0, True)
+        _, lg = self._run(codes, order, words, None, None, 1.0, 1)
         return lg.view(B, 32, 32, 512).permute(0, 3, 1, 2).contiguous()

@@ -1,6 +1,8 @@
-"""GPU parity of the activation-cached lmconv sampler (csrc/lmconv.cu) against the fp32 CPU oracle
-(oracle/lmconv_ref.py, pinned to the reference's OurPixelCNN).  Weights are bf16 in the kernel (fp32 accumulate):
-logits agree to 3% of the logit spread; drawn tokens are checked under teacher forcing with a mismatch budget,
+"""GPU parity of the wavefront tensor-core lmconv sampler (csrc/lmconv_tc.cu) against the fp32 CPU oracle
+(oracle/lmconv_ref.py, pinned to the reference's OurPixelCNN).  The kernel multiplies fp16 operands (weights and the
+cached concat_elu activations of all 33 masked convolutions) with fp32 accumulation, PONO / gates / residual stream in
+fp32.  Stated tolerance: logits within 0.5% of the logit spread (max) and 0.3% of the logit standard deviation (rms)
+(measured: 0.07% / 0.12%); drawn tokens are checked under teacher forcing with a 1.5% mismatch budget (measured 0.6%),
 because a categorical draw is discontinuous in the logits."""
 import os
 import sys
@@ -47,8 +49,8 @@ def test_teacher_forced_logits(env):
         ref = lmconv_ref.lmconv_logits(sd, data, *mf)
     err = (out - ref).abs()
     print("lmconv logits: max err %.4f rms %.5f (logit std %.3f)" % (err.max().item(), err.pow(2).mean().sqrt().item(), ref.std().item()))
-    assert err.max().item() <= 0.03 * (ref.max() - ref.min()).item()
-    assert err.pow(2).mean().sqrt().item() <= 0.01 * ref.std().item()
+    assert err.max().item() <= 0.005 * (ref.max() - ref.min()).item()
+    assert err.pow(2).mean().sqrt().item() <= 0.003 * ref.std().item()
 
 
 def test_sampling_is_consistent_with_the_oracle(env):
@@ -79,7 +81,7 @@ def test_sampling_is_consistent_with_the_oracle(env):
                 tot += 1
                 k += 1
     print("sampled tokens: %d, disagreeing with the oracle's draw: %d (%.2f%%)" % (tot, bad, 100.0 * bad / tot))
-    assert tot == int(sm.sum()) and bad <= 0.03 * tot
+    assert tot == int(sm.sum()) and bad <= 0.015 * tot
 
 
 def test_first_tokens_match_reference_style_sampling(env):

@@ -268,6 +268,10 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
                      int n_levels, long long* codes, const float* uniforms, int uniforms_stride, float temperature,
                      float* logits_out, void* cache, size_t cache_bytes, void* stream);
 
+/* Developer aid: CTA 0 of every lmconv launch writes clock64 timestamps of its pipeline events into this device
+ * buffer of 8 x 1024 int64 (NULL switches it off).  Not part of the product path. */
+void ps_lmconv_tc_set_trace(void* dev_buffer);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels  are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;
  * ps_timing_collect(NULL, ...) returns the sum over all names and releases the events. */

@@ -45,7 +45,6 @@ constexpr int TC_STAGES = PS_LMCONV_STAGES;
 constexpr int TC_A_BYTES = 128 * 128;  // 128 rows x 64 fp16
 constexpr int TC_W_BYTES = 160 * 128;  // up to 160 output channels x 64 fp16
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_W_BYTES;
-constexpr int TC_LAG = 4;  // gather groups in flight per thread
 constexpr int LMT_F = 80;
 constexpr int LMT_CELLS = 1024;
 constexpr int LMT_TENSORS = 33;
@@ -53,8 +52,37 @@ constexpr int LMT_ACT = 240;     // fp16 per (tensor, cell): elu(x) | elu(-x) | 
 constexpr int LMT_CLASSES = 512;
 constexpr int COL_OG = 400;      // TMEM columns [400, 480): the row's residual stream (fp32)
 constexpr int TC_NOPS = 18;
+constexpr int TC_MAX_CHUNKS = 728;
 
 enum { A_GATHER = 0, A_CENTRE = 1, A_EPILOGUE = 2 };
+
+// ps_lmconv_chunk in 8 bytes.  x: w_off16 (24) | w_rows / 8 (5) | a_kind (2);  y: a_tensor (6) | mask (2) | cin == 160 (1)
+// | kc (5) | reads the raw third of the cache row (1) | d_col / 16 (5) | flags (6)
+struct Chunk {
+  uint32_t w_off16;
+  int w_rows, a_kind, a_tensor, mask, cin8, kc, ch_off8, d_col, flags;
+};
+__device__ __forceinline__ uint2 pack_chunk(const ps_lmconv_chunk& c) {
+  uint2 r;
+  r.x = (c.w_off16 & 0xffffffu) | ((uint32_t)(c.w_rows >> 3) << 24) | ((uint32_t)c.a_kind << 29);
+  r.y = (uint32_t)c.a_tensor | ((uint32_t)c.mask << 6) | ((uint32_t)(c.cin8 == 20) << 8) | ((uint32_t)c.kc << 9) |
+        ((uint32_t)(c.ch_off8 != 0) << 14) | ((uint32_t)(c.d_col >> 4) << 15) | ((uint32_t)c.flags << 20);
+  return r;
+}
+__device__ __forceinline__ Chunk unpack_chunk(uint2 r) {
+  Chunk c;
+  c.w_off16 = r.x & 0xffffffu;
+  c.w_rows = (int)((r.x >> 24) & 31u) << 3;
+  c.a_kind = (int)(r.x >> 29) & 3;
+  c.a_tensor = (int)(r.y & 63u);
+  c.mask = (int)(r.y >> 6) & 3;
+  c.cin8 = ((r.y >> 8) & 1u) ? 20 : 10;
+  c.kc = (int)(r.y >> 9) & 31;
+  c.ch_off8 = ((r.y >> 14) & 1u) ? 20 : 0;
+  c.d_col = (int)((r.y >> 15) & 31u) << 4;
+  c.flags = (int)(r.y >> 20) & 63;
+  return c;
+}
 enum { FORM_NONE = 0, FORM_PAIR = 1, FORM_RAW = 2 };
 enum { ROW_SAMPLED = 1u << 16, ROW_LOGITS = 1u << 17, ROW_VALID = 1u << 18 };
 
@@ -70,17 +98,27 @@ struct TcParams {
   __half* act;
   const ps_lmconv_row* rows;
   int row_begin, row_end;
+  int rows_per_cta;  // 16, 32, 64 or 128 rows of the 128-row UMMA tile carry work (small levels spread over more SMs)
   long long* codes;
   const float* uniforms;
   int ustride;
   float inv_temperature;
   float* logits_out;
+  int debug;         // developer aid (PS_TC_DEBUG): bit0 skip the weight copies, bit1 skip the gather copies (timing only)
+  long long* trace;  // developer aid: clock64 timestamps of CTA 0 (ps_lmconv_tc_set_trace), or null
 };
+
+#define TC_TRACE(slot, idx)                                                   \
+  do {                                                                        \
+    if (p.trace && blockIdx.x == 0) p.trace[(slot) * 1024 + (idx)] = clock64(); \
+  } while (0)
 
 struct TcSmem {
   uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[3], ctr[2];
   uint32_t tmem_slot, pad_;
   ps_lmconv_row rows[128];
+  uint4 rowtab[128];  // per tile row, for the gather warps: cache base address (x, y), packed mask words (z)
+  uint2 sched[TC_MAX_CHUNKS];  // the chunk schedule, packed (a dependent global load per chunk would pace every role)
 };
 
 // Operands are fp16, not bf16: every activation that reaches a multiply is O(1) (PONO outputs, their ELUs, the
@@ -97,6 +135,22 @@ __device__ __forceinline__ void celu(float x, float& p, float& n) {
   const float e = ax < 0.03125f ? -ax * (1.0f - 0.5f * ax * (1.0f - 0.33333333f * ax)) : __expf(-ax) - 1.0f;  // expm1(-|x|)
   p = x > 0.0f ? x : e;
   n = x > 0.0f ? e : -x;
+}
+
+// v[0..16) += b[0..16) with four 16-byte loads (every bias block starts on a 16-byte boundary)
+__device__ __forceinline__ void add_bias16(float* v, const float* b) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(b + i));
+    v[i] += f.x;
+    v[i + 1] += f.y;
+    v[i + 2] += f.z;
+    v[i + 3] += f.w;
+  }
+}
+__device__ __forceinline__ void add_bias80(float* v, const float* b) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) add_bias16(v + 16 * j, b + 16 * j);
 }
 
 // positional normalisation over the 80 channels held by this thread (layers.py:224-236, unbiased variance)
@@ -135,7 +189,9 @@ struct Epi {
   __device__ __forceinline__ void acquire(int g) const { mbar_wait(&sm->ctr[g & 1], (uint32_t)(g >> 1) & 1u); }
   __device__ __forceinline__ void publish(int first, int count) const {
     fence_proxy_async();
-    for (int c = first; c < first + count; ++c) mbar_arrive(&sm->full[c % TC_STAGES]);
+    __syncwarp();
+    if ((threadIdx.x & 31) < 8)
+      for (int c = first; c < first + count; ++c) mbar_arrive(&sm->full[c % TC_STAGES]);
   }
   __device__ __forceinline__ void sts16(int first, int kgg, uint4 v) const {  // kgg = group index over the GEMM's centre K
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_addr(first + (kgg >> 3), kgg & 7)), "r"(v.x), "r"(v.y),
@@ -185,10 +241,13 @@ struct Epi {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   TcSmem& sm = *reinterpret_cast<TcSmem*>(tiles + (size_t)TC_STAGES * TC_STAGE_BYTES);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = p.row_begin + blockIdx.x * 128;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the shuffle tells the compiler the warp index is warp-uniform: role branches become uniform branches and the
+  // issuing roles' descriptor arithmetic can stay in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int row0 = p.row_begin + blockIdx.x * p.rows_per_cta;
 
   if (tid < 128) {
     ps_lmconv_row ri;
@@ -196,13 +255,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     ri.w01 = 0;
     ri.w2_flags = 0;
     ri.uidx = 0;
-    if (row0 + tid < p.row_end) ri = p.rows[row0 + tid];
+    if (tid < p.rows_per_cta && row0 + tid < p.row_end) ri = p.rows[row0 + tid];
     sm.rows[tid] = ri;
   }
+  for (int i = tid; i < p.n_total; i += TC_THREADS) sm.sched[i] = pack_chunk(p.chunks[i]);
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < TC_STAGES; ++s) {
-        mbar_init(&sm.full[s], 129);  // 128 row writers (gather or epilogue) + the weight producer
+        mbar_init(&sm.full[s], 33);  // 32 arrivals of the row writers (one gather warp, or 8 lanes of each epilogue warp) + the weight producer
         mbar_init(&sm.empty[s], 1);
       }
       for (int i = 0; i < 3; ++i) mbar_init(&sm.acc_full[i], 1);
@@ -214,124 +274,134 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   }
   tc_fence_before();
   const int need_logits =
-      __syncthreads_or(tid < 128 && row0 + tid < p.row_end && (p.rows[row0 + tid].w2_flags & (ROW_SAMPLED | ROW_LOGITS)));
+      __syncthreads_or(tid < p.rows_per_cta && row0 + tid < p.row_end &&
+                       (p.rows[row0 + tid].w2_flags & (ROW_SAMPLED | ROW_LOGITS)));
   tc_fence_after();
-  const uint32_t tmem_base = sm.tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, sm.tmem_slot, 0);
+  if (tid == 0) TC_TRACE(7, 0);
 #ifdef PS_TC_DEBUG
   if (tid == 0 && blockIdx.x == 0) printf("lmconv_tc: full[0] at smem 0x%x, rows %d..%d need_logits %d\n", smem_u32(&sm.full[0]), p.row_begin, p.row_end, need_logits);
 #endif
   const int nchunks = need_logits ? p.n_total : p.n_body;
 
   if (warp == 0) {
-    // ===== weight producer =====
-    if (lane == 0) {
+    // ===== weight producer: whole warp, warp-uniform values, one elected lane issues (see umma_f16_kblock) =====
+    {
+      int s = 0;
+      uint32_t ph = 1;
       for (int i = 0; i < nchunks; ++i) {
-        const ps_lmconv_chunk ch = p.chunks[i];
-        const int s = i % TC_STAGES;
-        mbar_wait(&sm.empty[s], ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
-        const uint32_t bytes = (uint32_t)ch.w_rows * 128u;
-        mbar_expect_tx(&sm.full[s], bytes);
-        bulk_load(tiles + (size_t)s * TC_STAGE_BYTES + TC_A_BYTES, p.wblob + (size_t)ch.w_off16 * 16, bytes, &sm.full[s]);
+        uint2 raw = sm.sched[i];
+        raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
+        mbar_wait(&sm.empty[s], ph);
+        if (lane == 0) TC_TRACE(3, i);
+        const uint32_t bytes = ((raw.x >> 24) & 31u) << 10;  // w_rows * 128
+        if (p.debug & 1) {
+          if (lane == 0) mbar_arrive(&sm.full[s]);
+        } else {
+          bulk_load_elect(tiles + (size_t)s * TC_STAGE_BYTES + TC_A_BYTES, p.wblob + (size_t)(raw.x & 0xffffffu) * 16, bytes,
+                          &sm.full[s]);
+        }
+        if (++s == TC_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    for (int i = 0; i < nchunks; ++i) {
-      const ps_lmconv_chunk ch = p.chunks[i];
-      const int s = i % TC_STAGES;
-      mbar_wait(&sm.full[s], (uint32_t)(i / TC_STAGES) & 1u);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES);
-        const uint32_t b = a + TC_A_BYTES;
-        const uint32_t idesc = umma_idesc_f16(ch.w_rows);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + ch.d_col, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc,
-                    ((ch.flags & 1) | k) ? 1u : 0u);
-        umma_commit(&sm.empty[s]);
-        if (ch.flags & 2) umma_commit(&sm.acc_full[(ch.flags >> 2) & 3]);
-        if (ch.flags & 16) umma_commit(&sm.ctr[(ch.flags >> 5) & 1]);
+    // ===== MMA issuer: the whole warp runs the loop with warp-uniform values; one elected lane issues =====
+    {
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
+      const uint32_t idesc0 = umma_idesc_f16(0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nchunks; ++i) {
+        uint2 raw = sm.sched[i];
+        raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
+        raw.y = __shfl_sync(0xffffffffu, raw.y, 0);
+        mbar_wait(&sm.full[s], ph);
+        if (!(p.debug & 8)) fence_proxy_async();
+        tc_fence_after();
+        if (lane == 0) TC_TRACE(0, i);
+        const uint32_t flags = raw.y >> 20;
+        const uint32_t idesc = idesc0 | (((raw.x >> 24) & 31u) << 17);       // N >> 3 = w_rows / 8
+        const uint32_t d = tmem_base + (((raw.y >> 15) & 31u) << 4);          // d_col
+        const uint32_t a_lo = a_lo0 + (uint32_t)s * (TC_STAGE_BYTES >> 4);
+        umma_f16_kblock(d, a_lo, a_lo + (TC_A_BYTES >> 4), idesc, flags & 1u, &sm.empty[s]);
+        if (flags & 2u) umma_commit_elect(&sm.acc_full[(flags >> 2) & 3u]);
+        if (flags & 16u) umma_commit_elect(&sm.ctr[(flags >> 5) & 1u]);
+        if (++s == TC_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      __syncwarp();
     }
   } else if (warp >= 6) {
-    // ===== gather producers: thread -> 16-byte group g of rows rsub, rsub + 16, ... =====
+    // ===== gather producers: warp w fills every 4th gathered chunk on its own =====
+    // A chunk is 128 rows x 8 groups of 16 bytes.  Lane -> group g = lane & 7 of rows rs, rs + 4, ... (rs = lane >> 3),
+    // so eight lanes read one contiguous 128-byte segment.  Whatever depends on the row only (cache base address,
+    // the three mask words packed into one register: bit m*9+tap, bit 27 = row valid) sits in a shared-memory
+    // table; per chunk a lane derives ONE (tap, channel group) from the descriptor, per row it tests one bit, adds
+    // one offset and issues one zero-filling cp.async.  One warp per chunk keeps the per-chunk fixed cost (descriptor,
+    // barrier wait, arrival) off the other three warps, which are busy with the next chunks.
     const int t = tid - 192;
-    const int g = t & 7, rsub = t >> 3;
-    int bcs[8];
-    uint32_t w01[8], w2f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const ps_lmconv_row ri = sm.rows[j * 16 + rsub];
-      bcs[j] = ri.bc;
-      w01[j] = ri.w01;
-      w2f[j] = ri.w2_flags;
+    {
+      const ps_lmconv_row ri = sm.rows[t];
+      const bool v = (ri.w2_flags & ROW_VALID) != 0;
+      const unsigned long long base =
+          (unsigned long long)p.act +
+          (v ? ((size_t)(ri.bc >> 10) * LMT_TENSORS * LMT_CELLS + (ri.bc & 1023)) * (LMT_ACT * 2) : 0);
+      const uint32_t w27 =
+          v ? ((ri.w01 & 0x1ffu) | (((ri.w01 >> 16) & 0x1ffu) << 9) | ((ri.w2_flags & 0x1ffu) << 18) | (1u << 27)) : 0u;
+      sm.rowtab[t] = make_uint4((uint32_t)base, (uint32_t)(base >> 32), w27, 0u);
     }
-    int fifo[TC_LAG];
-    int nq = 0;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four gather warps
+    const int gw = warp - 6, g = lane & 7, rs = lane >> 3;
+    const uint32_t dst_even = smem_u32(tiles) + rs * 128 + ((g ^ rs) << 4);        // rows rs + 8m
+    const uint32_t dst_odd = smem_u32(tiles) + (rs + 4) * 128 + ((g ^ (rs + 4)) << 4);  // rows rs + 4 + 8m
+    const int npair = p.rows_per_cta >> 3;  // row pairs (rs + 8m, rs + 4 + 8m) of this lane
+    int seen = 0;                            // gathered chunks so far: this warp takes those with seen % 4 == gw
     for (int i = 0; i < nchunks; ++i) {
-      const ps_lmconv_chunk ch = p.chunks[i];
-      if (ch.a_kind == A_EPILOGUE) {
-        // end of this GEMM's gathered chunks: publish everything still in flight, or the ring could never drain
-        // (the next stage to fill may be one this thread has not yet signalled)
-        if (nq) {
-          cp_async_wait<0>();
-          fence_proxy_async();
-#pragma unroll
-          for (int q = TC_LAG - 1; q >= 0; --q)
-            if (q < nq) mbar_arrive(&sm.full[fifo[q]]);
-          nq = 0;
-        }
-        continue;
-      }
+      const Chunk ch = unpack_chunk(sm.sched[i]);
+      if (ch.a_kind == A_EPILOGUE) continue;
+      if ((seen++ & 3) != gw) continue;
       const int s = i % TC_STAGES;
-      mbar_wait(&sm.empty[s], ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
       const int kg = ch.kc * 8 + g;
-      int c8, tap = 4, doff = 0;
-      bool kvalid;
+      int bitpos, off;  // mask bit to test, byte offset from the row's base
       if (ch.a_kind == A_GATHER) {
-        const int slot = kg / ch.cin8;
-        c8 = kg - slot * ch.cin8;
-        tap = slot + (slot >= 4 ? 1 : 0);
+        const int slot = ch.cin8 == 20 ? kg / 20 : kg / 10;
+        const int c8 = kg - slot * ch.cin8;
+        const int tap = slot + (slot >= 4 ? 1 : 0);
+        const int tr = (tap * 11) >> 5;  // tap / 3 for tap < 9
         const int dil = ch.mask == 2 ? 2 : 1;
-        doff = ((tap / 3 - 1) * 32 + (tap % 3 - 1)) * dil;
-        kvalid = true;
+        bitpos = ch.mask * 9 + tap;
+        off = (((tr - 1) * 32 + (tap - 3 * tr - 1)) * dil + ch.a_tensor * LMT_CELLS) * (LMT_ACT * 2) + (ch.ch_off8 + c8) * 16;
       } else {
-        c8 = kg;
-        kvalid = kg < ch.cin8;
+        bitpos = kg < ch.cin8 ? 27 : 31;
+        off = ch.a_tensor * LMT_CELLS * (LMT_ACT * 2) + (ch.ch_off8 + kg) * 16;
       }
-      const size_t toff = (size_t)ch.a_tensor * LMT_CELLS * LMT_ACT + (size_t)(ch.ch_off8 + c8) * 8;
-      const uint32_t abase = smem_u32(tiles + (size_t)s * TC_STAGE_BYTES);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int row = j * 16 + rsub;
-        bool ok = kvalid && (w2f[j] & ROW_VALID);
-        if (ch.a_kind == A_GATHER) {
-          const uint32_t w = ch.mask == 0 ? (w01[j] & 0xffffu) : (ch.mask == 1 ? (w01[j] >> 16) : (w2f[j] & 0xffffu));
-          ok = ok && ((w >> tap) & 1u);
+      mbar_wait(&sm.empty[s], ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+      if (lane == 0) TC_TRACE(1, i);
+      const uint32_t soff = s * TC_STAGE_BYTES;
+      if (!(p.debug & 2)) {
+#pragma unroll 4
+        for (int m = 0; m < npair; ++m) {
+          const uint4 r0 = sm.rowtab[rs + 8 * m], r1 = sm.rowtab[rs + 4 + 8 * m];
+          const uint32_t ok0 = (r0.z >> bitpos) & 1u, ok1 = (r1.z >> bitpos) & 1u;
+          const unsigned long long b0 = ((unsigned long long)r0.y << 32 | r0.x) + (ok0 ? off : 0);
+          const unsigned long long b1 = ((unsigned long long)r1.y << 32 | r1.x) + (ok1 ? off : 0);
+          cp_async16_zfill(dst_even + soff + m * 1024, (const void*)b0, ok0 << 4);
+          cp_async16_zfill(dst_odd + soff + m * 1024, (const void*)b1, ok1 << 4);
         }
-        const int b = bcs[j] >> 10, cell = bcs[j] & 1023;
-        const __half* src =
-            ok ? p.act + ((size_t)b * LMT_TENSORS * LMT_CELLS + cell + doff) * LMT_ACT + toff : p.act;
-        cp_async16_zfill(abase + row * 128 + ((g ^ (row & 7)) << 4), src, ok ? 16u : 0u);
       }
-      cp_async_commit();
-#pragma unroll
-      for (int q = TC_LAG - 1; q > 0; --q) fifo[q] = fifo[q - 1];
-      fifo[0] = s;
-      if (++nq == TC_LAG) {
-        cp_async_wait<TC_LAG - 1>();
-        fence_proxy_async();
-        mbar_arrive(&sm.full[fifo[TC_LAG - 1]]);
-        --nq;
-      }
+      // asynchronous completion: the stage's full barrier gets this lane's arrival when its copies have landed, so
+      // the warp never blocks on data and every free stage of the ring is in flight (the MMA warp orders the
+      // landed generic-proxy writes before its async-proxy reads with fence.proxy.async)
+      if (p.debug & 32)
+        mbar_arrive(&sm.full[s]);  // timing experiment (with bit 1): how long does the asynchronous arrival itself take?
+      else
+        cp_async_arrive_noinc(&sm.full[s]);
+      if (lane == 0) TC_TRACE(2, i);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-#pragma unroll
-    for (int q = TC_LAG - 1; q >= 0; --q)
-      if (q < nq) mbar_arrive(&sm.full[fifo[q]]);
   } else {
     // ===== epilogue: one thread per row =====
     Epi e;
@@ -351,7 +421,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     {
       float v[LMT_F];
 #pragma unroll
-      for (int i = 0; i < LMT_F; ++i) v[i] = __ldg(bias + p.b_uinit + i);
+      for (int i = 0; i < LMT_F; ++i) v[i] = 0.f;
+      add_bias80(v, bias + p.b_uinit);
       const uint32_t w0 = ri.w01 & 0x1ffu;
       for (int tap = 0; tap < 9; ++tap) {
         if (!((w0 >> tap) & 1u)) continue;
@@ -392,42 +463,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         {  // x = PONO(conv_input(concat_elu(og))) [+ nin_skip(concat_elu(a))]
           const uint32_t col0 = (uint32_t)(g & 1) * 160u;
           mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
+          if (e.r == 0) TC_TRACE(4, g);
           tc_fence_after();
           float x[LMT_F];
 #pragma unroll
           for (int j = 0; j < 5; ++j) tmem_ld16_nowait(e.tlane + col0 + 16 * j, x + 16 * j);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < LMT_F; ++i) x[i] += __ldg(bias + op.b_in + i);
+          add_bias80(x, bias + op.b_in);
           pono80(x);
           if (op.a >= 0) {
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
               float sk[16];
               tmem_ld16_nowait(e.tlane + col0 + 80 + 16 * j, sk);
+              add_bias16(x + 16 * j, bias + op.b_skip + 16 * j);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) x[16 * j + i] += sk[i] + __ldg(bias + op.b_skip + 16 * j + i);
+              for (int i = 0; i < 16; ++i) x[16 * j + i] += sk[i];
             }
           }
           tc_fence_before();
           const int first = p.epi_first[g + 1];
           e.acquire(g + 1);
+          if (e.r == 0) TC_TRACE(6, g);
 #pragma unroll
           for (int j = 0; j < 5; ++j) e.emit16(FORM_PAIR, first, j, x + 16 * j, op.mid, false);
           e.publish(first, 3);
+          if (e.r == 0) TC_TRACE(5, g);
           ++g;
         }
         {  // y = conv_out(concat_elu(x)); og += PONO(y[:80]) * sigmoid(y[80:])
           const uint32_t col0 = (uint32_t)(g & 1) * 160u;
           mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
+          if (e.r == 0) TC_TRACE(4, g);
           tc_fence_after();
           float a[LMT_F];
 #pragma unroll
           for (int j = 0; j < 5; ++j) tmem_ld16_nowait(e.tlane + col0 + 16 * j, a + 16 * j);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < LMT_F; ++i) a[i] += __ldg(bias + op.b_out + i);
+          add_bias80(a, bias + op.b_out);
           pono80(a);
           const int first = next_count ? p.epi_first[g + 1] : 0;
           if (next_count) e.acquire(g + 1);
@@ -437,29 +511,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
             tmem_ld16_nowait(e.tlane + col0 + 80 + 16 * j, gt);
             tmem_ld16_nowait(e.tlane + COL_OG + 16 * j, o);
             tmem_ld_wait();
+            add_bias16(gt, bias + op.b_out + 80 + 16 * j);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float gv = gt[i] + __ldg(bias + op.b_out + 80 + 16 * j + i);
-              o[i] = fmaf(a[16 * j + i], 1.0f / (1.0f + __expf(-gv)), o[i]);
-            }
+            for (int i = 0; i < 16; ++i) o[i] = fmaf(a[16 * j + i], 1.0f / (1.0f + __expf(-gt[i])), o[i]);
             tmem_st16_nowait(e.tlane + COL_OG + 16 * j, o);
             e.emit16(next_form, first, j, o, op.out, true);
           }
           tmem_st_wait();
           tc_fence_before();
           e.publish(first, next_count);
+          if (e.r == 0) TC_TRACE(5, g);
           ++g;
         }
       } else {  // dilated masked conv on the raw stream + PONO becomes the new stream
         const uint32_t col0 = (uint32_t)(g & 1) * 160u;
         mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
+        if (e.r == 0) TC_TRACE(4, g);
         tc_fence_after();
         float x[LMT_F];
 #pragma unroll
         for (int j = 0; j < 5; ++j) tmem_ld16_nowait(e.tlane + col0 + 16 * j, x + 16 * j);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < LMT_F; ++i) x[i] += __ldg(bias + op.b_in + i);
+        add_bias80(x, bias + op.b_in);
         pono80(x);
         const int first = next_count ? p.epi_first[g + 1] : 0;
         if (next_count) e.acquire(g + 1);
@@ -471,6 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         tmem_st_wait();
         tc_fence_before();
         e.publish(first, next_count);
+        if (e.r == 0) TC_TRACE(5, g);
         ++g;
       }
     }
@@ -552,6 +626,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     }
   }
   __syncthreads();
+  if (tid == 0) TC_TRACE(7, 1);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -559,7 +634,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
 
 using namespace ps;
 
+static thread_local long long* g_tc_trace = nullptr;
+
 extern "C" {
+
+// developer aid (tools/trace_lmconv.py): device buffer of 8 x 1024 int64 receiving CTA 0's timestamps, or NULL
+void ps_lmconv_tc_set_trace(void* dev_buffer) { g_tc_trace = (long long*)dev_buffer; }
 
 size_t ps_lmconv_tc_cache_bytes(int B) {
   return (size_t)(B > 0 ? B : 0) * LMT_TENSORS * LMT_CELLS * LMT_ACT * sizeof(__half);
@@ -647,6 +727,7 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   PS_CHECK_ARG(plan && plan->wblob && plan->chunks && plan->w_uinit && plan->bias && codes && cache);
   PS_CHECK_ARG(B >= 0 && n_levels >= 0 && temperature > 0.0f);
   PS_CHECK_ARG(plan->n_chunks_body > 0 && plan->n_chunks_total >= plan->n_chunks_body);
+  PS_CHECK_ARG(plan->n_chunks_total <= TC_MAX_CHUNKS);
   if (B == 0 || n_levels == 0) return PS_OK;
   PS_CHECK_ARG(rows_dev && level_offsets_host);
   PS_CHECK_ARG(uniforms || logits_out);  // sampling needs the uniform numbers
@@ -672,6 +753,8 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   p.ustride = uniforms_stride;
   p.inv_temperature = 1.0f / temperature;
   p.logits_out = logits_out;
+  p.trace = g_tc_trace;
+  p.debug = getenv("PS_TC_DEBUG") ? atoi(getenv("PS_TC_DEBUG")) : 0;
   const size_t smem_bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcSmem);
   static thread_local int attr_dev = -1;
   int dev = 0;
@@ -680,13 +763,20 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
     PS_CUDA(cudaFuncSetAttribute(lmconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr_dev = dev;
   }
+  int sms = 148;
+  PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   PS_TIME_BEGIN("lmconv_tc_kernel", (cudaStream_t)stream);
   for (int l = 0; l < n_levels; ++l) {
     const int r0 = level_offsets_host[l], r1 = level_offsets_host[l + 1];
     if (r1 <= r0) continue;
+    // a level is latency bound per CTA (a 36-GEMM dependent chain), so small levels use fewer rows of each
+    // 128-row tile and more SMs; full tiles once the level fills the GPU
+    int rpc = 32;
+    while (rpc < 128 && (r1 - r0 + rpc - 1) / rpc > sms) rpc *= 2;
     p.row_begin = r0;
     p.row_end = r1;
-    lmconv_tc_kernel<<<(r1 - r0 + 127) / 128, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    p.rows_per_cta = rpc;
+    lmconv_tc_kernel<<<(r1 - r0 + rpc - 1) / rpc, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
     PS_LAUNCHED();
   }
   PS_TIME_END((cudaStream_t)stream);

@@ -23,23 +23,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // so the kernel terminates (with garbage) instead of hanging the device; the host checks g_wedge after the launch.
 static __device__ unsigned int g_wedge[8];
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
-  long long t0 = 0;
+  // no suspend-time hint: with one, ptxas emits NANOSLEEP.SYNCS <hint> after a failed check and the wake-up costs
+  // hundreds of ns per hand-off, which paced every producer/consumer ring at ~0.3 us per stage
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done;
+}
+
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
   for (int spins = 0;; ++spins) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x4000;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (spins == 64) t0 = clock64();
-    if ((spins & 15) == 15 && *(volatile unsigned int*)&g_wedge[0]) return;
-    if (spins > 64 && (spins & 255) == 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 63) == 63) {
+      if (*(volatile unsigned int*)&g_wedge[0]) return;
       if (clock64() - t0 > 2000000000ll) {
         if (atomicCAS(&g_wedge[0], 0u, 1u) == 0u) {
           g_wedge[1] = blockIdx.x;
@@ -52,6 +57,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       }
     }
   }
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (int spins = 0; spins < 4096; ++spins)
+    if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);  // ~ms without progress: start the wedge watchdog
 }
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
@@ -79,9 +91,25 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// whole warp, warp-uniform operands: one elected lane arms the barrier with the byte count and issues the copy
+__device__ __forceinline__ void bulk_load_elect(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+      "}" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
 // 16-byte Ampere-style async copy with zero fill (src_bytes = 0 or 16)
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"((uint64_t)src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -114,6 +142,64 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Same MMA with the shared-memory descriptors given as (low word, shared high word): the issuing thread keeps the
+// per-stage low words in registers and adds 2 per 32-byte K step, so a K block costs a handful of instructions.
+// desc_hi = SBO 1024 B | version 1 | SWIZZLE_128B; desc_lo = (address >> 4) | LBO 1.
+constexpr uint32_t UMMA_DESC_HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
+// One K block (64 fp16 = four K=16 MMAs over one 128-byte-swizzled stage) + its commit, executed by the WHOLE warp
+// with warp-uniform operands; elect.sync predicates the tcgen05 instructions themselves.  Keeping control flow and
+// operands uniform lets ptxas hold the descriptors in uniform registers -- under `if (lane == 0)` every operand of
+// every UTCHMMA goes through a chain of dependent R2UR moves, ~100 cycles per MMA, which paced the whole ring.
+__device__ __forceinline__ void umma_f16_kblock(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc,
+                                                uint64_t* commit_bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128), "r"(smem_u32(commit_bar))
+      : "memory");
+}
+// whole warp, one elected lane commits
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

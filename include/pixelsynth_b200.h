@@ -196,7 +196,8 @@ int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, int* dist_hos
  * Replaces models/lmconv/sample.py:8-73 (sample) + models/lmconv/model.py:110-155 (OurPixelCNN.forward, called
  * once per token there).  The masks make the network causal in generation order, so every cell's activation
  * column is computed once; cells that are not masked-in neighbours of each other are independent, so the
- * dependency DAG is levelled (ps_lmconv_levels_host) and each level is one launch over (image, cell) rows.
+ * dependency DAG is levelled (ps_lmconv_levels_host) and ONE launch runs all levels: tiles of up to 128 (image,
+ * cell) rows are handed out in level order and synchronise through progress words in global memory.
  *
  * ps_lmconv_plan: the network as the kernel consumes it (built by pixelsynth_b200/lmconv.py from the reference's
  * state dict):
@@ -205,14 +206,17 @@ int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, int* dist_hos
  *   chunks  the static K-chunk schedule.  a_kind 0: rows gathered from cached tensor a_tensor through mask
  *           `mask` (0 = A dil 1, 1 = B dil 1, 2 = B dil 2), K = (non-centre tap slot, channel), chunk kc of it,
  *           channels start at ch_off8*8 of the 240-wide cache row; a_kind 1: the row's own cell of a_tensor
- *           (nin_skip); a_kind 2: written by the epilogue of the previous GEMM (the centre tap).
+ *           (nin_skip); a_kind 3: the centre tap, written into tensor memory by the epilogue of the previous
+ *           GEMM; a_kind 2: nin_out quarter 0, operand written into the chunk's ring stage by the last epilogue;
+ *           a_kind 4: nin_out quarters 1-3, which re-read quarter 0's operand.
  *           d_col = TMEM column of the accumulator, flags bit0 = accumulate, bit1 = last chunk of the GEMM,
- *           bits 2-3 = which accumulator barrier that completes (0/1 ping-pong, 2 = logits), bit4 = the stages of
- *           GEMM (bit5 parity)'s centre chunks are free once this chunk has been multiplied (it is the chunk
- *           PS_LMCONV_STAGES before the last centre chunk of that GEMM)
- *   epi_first[g]  index of the first a_kind-2 chunk of GEMM g (GEMMs in execution order; nin_out = 4 quarters)
+ *           bits 2-3 = which accumulator barrier that completes (0/1 ping-pong, 2 = logits), bit4 = first centre
+ *           chunk of its GEMM (the issuer waits for the epilogue's operand there); gemm = index of the chunk's
+ *           GEMM in execution order
+ *   epi_first[g]  index of the first centre chunk of GEMM g (GEMMs in execution order; nin_out = 4 quarters)
  *   ops     the 18 column operations after u_init (14 gated resnets, kind 0; 4 dilated convs + PONO, kind 1) with
  *           the ids (0..32) of the cached tensors they write (mid, out) and their bias offsets
+ *   raw_mask  bit t set: cached tensor t is also read un-activated (by a dilated convolution)
  * ps_lmconv_row: bc = image << 10 | cell; w01 = mask word A | mask word B << 16; w2_flags = mask word B-dil-2 |
  *           bit16 sampled | bit17 logits wanted | bit18 valid; uidx = index of the row's uniform number
  * ------------------------------------------------------------------------------------------------ */
@@ -230,7 +234,7 @@ typedef struct {
   uint16_t w_rows;
   uint8_t a_kind, a_tensor, mask, cin8, kc, ch_off8;
   uint16_t d_col;
-  uint8_t flags, pad;
+  uint8_t flags, gemm;
 } ps_lmconv_chunk;
 
 typedef struct {
@@ -249,26 +253,31 @@ typedef struct {
   const float* bias;   /* device */
   int b_uinit, b_nin;
   ps_lmconv_op ops[18];
+  unsigned long long raw_mask;
 } ps_lmconv_plan;
 
+/* device scratch ps_lmconv_tc_run needs for B images: activation cache + tile table + progress words */
 size_t ps_lmconv_tc_cache_bytes(int B);
 
 /* Host: rows of every dependency level, level by level (rows_out holds up to B*1024 rows, level_offsets
- * max_levels + 1 ints).  mode 0 = sampling (order (B,1024) i32, words (B,3,1024) u16, sample_mask (B,1024) u8 as
- * produced by ps_lmconv_glue_host; cells after an image's last sampled cell are skipped, images with nothing to
- * sample produce no rows); mode 1 = teacher-forced logits of all cells (one level, sample_mask may be NULL). */
+ * max_levels + 1 ints).  Levels come in two phases: first the known prefix (cells with no sampled cell among their
+ * ancestors), then from *first_b_level on the sampled cells and everything downstream of them, levelled among
+ * themselves.  mode 0 = sampling (order (B,1024) i32, words (B,3,1024) u16, sample_mask (B,1024) u8 as produced by
+ * ps_lmconv_glue_host; cells after an image's last sampled cell are skipped, images with nothing to sample
+ * produce no rows); mode 1 = teacher-forced logits of all cells (sample_mask may be NULL; every level is prefix). */
 int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t* sample_mask, int B, int mode,
-                          ps_lmconv_row* rows_out, int* level_offsets, int max_levels, int* n_levels);
+                          ps_lmconv_row* rows_out, int* level_offsets, int max_levels, int* n_levels,
+                          int* first_b_level);
 
-/* Device: runs the levels in order on `stream`.  codes (B,1024) i64: in = known codes, out = sampled cells filled;
- * uniforms (B,stride) f32: the k-th sampled cell (in generation order) of image b takes the first class whose
+/* Device: runs all levels in one launch on `stream`.  codes (B,1024) i64: in = known codes, out = sampled cells
+ * filled; uniforms (B,stride) f32: the k-th sampled cell (in generation order) of image b takes the first class whose
  * cumulative softmax(logits/temperature) exceeds uniforms[b][k]; logits_out (B,1024,512) f32 or NULL receives the
  * logits of rows flagged bit17; cache: ps_lmconv_tc_cache_bytes(B) bytes of device scratch. */
 int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* rows_dev, const int* level_offsets_host,
-                     int n_levels, long long* codes, const float* uniforms, int uniforms_stride, float temperature,
-                     float* logits_out, void* cache, size_t cache_bytes, void* stream);
+                     int n_levels, int first_b_level, long long* codes, const float* uniforms, int uniforms_stride,
+                     float temperature, float* logits_out, void* cache, size_t cache_bytes, void* stream);
 
-/* Developer aid: CTA 0 of every lmconv launch writes clock64 timestamps of its pipeline events into this device
+/* Developer aid: the last tile of every lmconv launch writes clock64 timestamps of its pipeline events into this device
  * buffer of 8 x 1024 int64 (NULL switches it off).  Not part of the product path. */
 void ps_lmconv_tc_set_trace(void* dev_buffer);
 

@@ -37,8 +37,8 @@ SIGNATURES = {
     "ps_tanh_residual": (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
     "ps_lmconv_glue_host": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "ps_lmconv_tc_cache_bytes": (c_sz, [c_i]),
-    "ps_lmconv_levels_host": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p]),
-    "ps_lmconv_tc_run": (c_i, [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_f, c_p, c_p, c_sz, c_p]),
+    "ps_lmconv_levels_host": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p]),
+    "ps_lmconv_tc_run": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_f, c_p, c_p, c_sz, c_p]),
     "ps_lmconv_tc_set_trace": (None, [c_p]),
     "ps_launch_count": (ctypes.c_longlong, []),
     "ps_launch_count_reset": (None, []),

@@ -12,19 +12,28 @@
 //      known prefix cells of all images at level 0, then wavefronts of mutually independent sampled cells -- is
 //      one launch in which each CTA drives a tile of 128 (image, cell) rows through the whole column.
 //
-// Per CTA: rows are the UMMA M dimension (one TMEM lane = one cell), output channels the N dimension, and
-// (tap, input channel) the K dimension, walked in 64-wide chunks through a 6-stage shared-memory ring:
+// Per CTA (one tile of up to 128 rows): rows are the UMMA M dimension (one TMEM lane = one cell), output channels
+// the N dimension, and (tap, input channel) the K dimension, walked in 64-wide chunks through a 6-stage
+// shared-memory ring:
 //   warp 0      streams the pre-swizzled fp16 weight tile of each chunk with cp.async.bulk (static schedule),
 //   warps 6-9   gather the neighbours' cached activations of each chunk with zero-filling cp.async (a masked-out
 //               tap is a zero row, so the mask costs no bandwidth),
 //   warp 1      issues tcgen05.mma (M=128, N=80/160/128, K=16) into two ping-pong TMEM accumulators,
 //   warps 2-5   epilogue, one thread per row: bias, PONO (a thread-local reduction over the 80 channels of its own
 //               TMEM lane), gate / residual (the residual stream lives in spare TMEM columns), concat_elu, the
-//               cache write, and the centre-tap operand chunks of the NEXT layer written straight into the ring
-//               -- the only data a layer needs from the previous one -- so the non-centre chunks of layer l+1
-//               are multiplied while the epilogue of layer l runs.
+//               cache write, and the centre-tap operand of the NEXT layer -- the only data a layer needs from the
+//               previous one -- written with tcgen05.st into TMEM columns the next layer's centre MMAs read as
+//               their A operand (A-from-TMEM form), so the epilogue never waits for the ring and the non-centre
+//               chunks of layer l+1 are multiplied while the epilogue of layer l runs,
+//   warp 10     publishes the tile's progress (cache tensors complete) to global memory.
 // After the last layer nin_out puts the 512 logits of each row in TMEM and the row's thread draws the token
 // (softmax / temperature, inverse CDF with the caller's uniform).
+//
+// ONE launch runs every level: CTAs take tiles (sorted by level) from an atomic ticket, so a tile only ever waits
+// for tiles that are already running or finished.  Layer j of a level needs the neighbours' layer j-1 columns, so
+// the levels of the known prefix run as a software pipeline two layers apart (a gather warp polls the previous
+// level's progress words before it reads the cache); a level that holds sampled cells additionally waits for the
+// previous level's tokens, because its first layer reads them.
 //
 // Layouts: activation cache fp16 (B, 33 tensors, 1024 cells, 240) = [elu(x) | elu(-x) | x]; weights fp16, one
 // 128-byte-swizzled K-major [cout][64] tile per chunk in schedule order (pixelsynth_b200/lmconv.py packs them).
@@ -40,8 +49,9 @@
 
 namespace ps {
 
-constexpr int TC_THREADS = 320;
-constexpr int TC_STAGES = PS_LMCONV_STAGES;
+constexpr int TC_THREADS = 352;
+constexpr int TC_STAGES = PS_LMCONV_STAGES;  // ring stages of a full 128-row tile
+constexpr int TC_MAX_STAGES = 12;            // a tile of fewer rows keeps a smaller A tile per stage and gets more stages
 constexpr int TC_A_BYTES = 128 * 128;  // 128 rows x 64 fp16
 constexpr int TC_W_BYTES = 160 * 128;  // up to 160 output channels x 64 fp16
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_W_BYTES;
@@ -50,30 +60,33 @@ constexpr int LMT_CELLS = 1024;
 constexpr int LMT_TENSORS = 33;
 constexpr int LMT_ACT = 240;     // fp16 per (tensor, cell): elu(x) | elu(-x) | x
 constexpr int LMT_CLASSES = 512;
-constexpr int COL_OG = 400;      // TMEM columns [400, 480): the row's residual stream (fp32)
+constexpr int COL_OG = 320;      // TMEM columns [320, 400): the row's residual stream (fp32)
+constexpr int COL_A = 400;       // TMEM columns [400, 496): centre-tap A operand of the next GEMM (192 fp16 per row)
+constexpr int PROG_DONE = 34;    // progress word of a finished tile: 33 cache tensors + the sampled tokens
 constexpr int TC_NOPS = 18;
 constexpr int TC_MAX_CHUNKS = 728;
 
-enum { A_GATHER = 0, A_CENTRE = 1, A_EPILOGUE = 2 };
+enum { A_GATHER = 0, A_CENTRE = 1, A_EPILOGUE = 2, A_TMEM = 3, A_REUSE = 4 };
 
-// ps_lmconv_chunk in 8 bytes.  x: w_off16 (24) | w_rows / 8 (5) | a_kind (2);  y: a_tensor (6) | mask (2) | cin == 160 (1)
-// | kc (5) | reads the raw third of the cache row (1) | d_col / 16 (5) | flags (6)
+// ps_lmconv_chunk in 8 bytes.  x: w_off16 (24) | w_rows / 8 (5) | a_kind (3);  y: a_tensor (6) | mask (2) | cin == 160 (1)
+// | kc (5) | reads the raw third of the cache row (1) | d_col / 16 (5) | flags (6) | GEMM index (6)
 struct Chunk {
   uint32_t w_off16;
-  int w_rows, a_kind, a_tensor, mask, cin8, kc, ch_off8, d_col, flags;
+  int w_rows, a_kind, a_tensor, mask, cin8, kc, ch_off8, d_col, flags, gemm;
 };
 __device__ __forceinline__ uint2 pack_chunk(const ps_lmconv_chunk& c) {
   uint2 r;
   r.x = (c.w_off16 & 0xffffffu) | ((uint32_t)(c.w_rows >> 3) << 24) | ((uint32_t)c.a_kind << 29);
   r.y = (uint32_t)c.a_tensor | ((uint32_t)c.mask << 6) | ((uint32_t)(c.cin8 == 20) << 8) | ((uint32_t)c.kc << 9) |
-        ((uint32_t)(c.ch_off8 != 0) << 14) | ((uint32_t)(c.d_col >> 4) << 15) | ((uint32_t)c.flags << 20);
+        ((uint32_t)(c.ch_off8 != 0) << 14) | ((uint32_t)(c.d_col >> 4) << 15) | ((uint32_t)(c.flags & 63) << 20) |
+        ((uint32_t)(c.gemm & 63) << 26);
   return r;
 }
 __device__ __forceinline__ Chunk unpack_chunk(uint2 r) {
   Chunk c;
   c.w_off16 = r.x & 0xffffffu;
   c.w_rows = (int)((r.x >> 24) & 31u) << 3;
-  c.a_kind = (int)(r.x >> 29) & 3;
+  c.a_kind = (int)(r.x >> 29) & 7;
   c.a_tensor = (int)(r.y & 63u);
   c.mask = (int)(r.y >> 6) & 3;
   c.cin8 = ((r.y >> 8) & 1u) ? 20 : 10;
@@ -81,41 +94,52 @@ __device__ __forceinline__ Chunk unpack_chunk(uint2 r) {
   c.ch_off8 = ((r.y >> 14) & 1u) ? 20 : 0;
   c.d_col = (int)((r.y >> 15) & 31u) << 4;
   c.flags = (int)(r.y >> 20) & 63;
+  c.gemm = (int)(r.y >> 26) & 63;
   return c;
 }
 enum { FORM_NONE = 0, FORM_PAIR = 1, FORM_RAW = 2 };
 enum { ROW_SAMPLED = 1u << 16, ROW_LOGITS = 1u << 17, ROW_VALID = 1u << 18 };
+// One tile = up to 128 consecutive rows of one level.  prev_first / prev_count: the tiles of the previous level;
+// wait_start: progress the previous level must have published before this tile does anything (0, all 33 cache
+// tensors, or PROG_DONE = its tokens as well).
+struct Tile {
+  int row_begin, nrows, prev_first, prev_count, wait_start, pad0, pad1, pad2;
+};
 
 struct TcParams {
   const unsigned char* wblob;
   const ps_lmconv_chunk* chunks;
   int n_body, n_total;
-  int epi_first[PS_LMCONV_MAX_GEMMS];
+  int logit_first;   // schedule index of the first nin_out chunk (quarter 0, kc 0)
   const __half* w_uinit;  // [9][513][80]
   const float* bias;
   int b_uinit, b_nin;
   ps_lmconv_op ops[TC_NOPS];
+  unsigned long long raw_mask;  // bit t: cached tensor t is read through its raw third (by a dilated convolution)
   __half* act;
   const ps_lmconv_row* rows;
-  int row_begin, row_end;
-  int rows_per_cta;  // 16, 32, 64 or 128 rows of the 128-row UMMA tile carry work (small levels spread over more SMs)
+  const Tile* tiles;
+  int n_tiles;
+  unsigned int* sync;  // [0] ticket counter, [16 + t] progress of tile t
   long long* codes;
   const float* uniforms;
   int ustride;
   float inv_temperature;
   float* logits_out;
   int debug;         // developer aid (PS_TC_DEBUG): bit0 skip the weight copies, bit1 skip the gather copies (timing only)
-  long long* trace;  // developer aid: clock64 timestamps of CTA 0 (ps_lmconv_tc_set_trace), or null
+  long long* trace;  // developer aid: clock64 timestamps of the LAST tile (ps_lmconv_tc_set_trace), or null
 };
 
-#define TC_TRACE(slot, idx)                                                   \
-  do {                                                                        \
-    if (p.trace && blockIdx.x == 0) p.trace[(slot) * 1024 + (idx)] = clock64(); \
+#define TC_TRACE(slot, idx)                                              \
+  do {                                                                   \
+    if (p.trace && traced) p.trace[(slot) * 1024 + (idx)] = clock64();   \
   } while (0)
 
 struct TcSmem {
-  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[3], ctr[2];
-  uint32_t tmem_slot, pad_;
+  uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[3], cfull;
+  uint32_t tmem_slot, step_count;
+  Tile tile;
+  int tile_index, pad_;
   ps_lmconv_row rows[128];
   uint4 rowtab[128];  // per tile row, for the gather warps: cache base address (x, y), packed mask words (z)
   uint2 sched[TC_MAX_CHUNKS];  // the chunk schedule, packed (a dependent global load per chunk would pace every role)
@@ -129,10 +153,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // concat_elu of one value: (elu(x), elu(-x)) with a single exponential
 __device__ __forceinline__ void celu(float x, float& p, float& n) {
-  const float ax = fabsf(x);
-  const float e = ax < 0.03125f ? -ax * (1.0f - 0.5f * ax * (1.0f - 0.33333333f * ax)) : __expf(-ax) - 1.0f;  // expm1(-|x|)
+  // expm1(-|x|) as exp - 1: the absolute error (~2e-7) is far below the fp16 rounding of the operand it becomes
+  const float e = exp2f_fast(-1.4426950408889634f * fabsf(x)) - 1.0f;
   p = x > 0.0f ? x : e;
   n = x > 0.0f ? e : -x;
 }
@@ -155,86 +184,135 @@ __device__ __forceinline__ void add_bias80(float* v, const float* b) {
 
 // positional normalisation over the 80 channels held by this thread (layers.py:224-236, unbiased variance)
 __device__ __forceinline__ void pono80(float* v) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LMT_F; ++i) s += v[i];
-  const float mean = s * (1.0f / LMT_F);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < LMT_F; ++i) {
-    const float d = v[i] - mean;
-    q = fmaf(d, d, q);
+  for (int i = 0; i < LMT_F; i += 4) {
+    s0 += v[i];
+    s1 += v[i + 1];
+    s2 += v[i + 2];
+    s3 += v[i + 3];
   }
-  const float inv = 1.0f / sqrtf(q * (1.0f / (LMT_F - 1)) + 1e-5f);
+  const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / LMT_F);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LMT_F; i += 4) {
+    const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
+    q0 = fmaf(d0, d0, q0);
+    q1 = fmaf(d1, d1, q1);
+    q2 = fmaf(d2, d2, q2);
+    q3 = fmaf(d3, d3, q3);
+  }
+  const float inv = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / (LMT_F - 1)) + 1e-5f);
 #pragma unroll
   for (int i = 0; i < LMT_F; ++i) v[i] = (v[i] - mean) * inv;
 }
 
-struct Epi {
-  unsigned char* tiles;
-  TcSmem* sm;
-  int r;            // tile row of this thread
-  uint32_t tlane;   // TMEM address of this thread's lane, column 0
-  bool valid;
-  __half* actrow;  // act + (b * 33 * 1024 + cell) * 240; tensor t adds t * 1024 * 240
+// progress words: written by one thread per tile (release), polled by the tiles of the next level (acquire)
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_cta_shared(const uint32_t* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_cta_shared_inc(uint32_t* p) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
 
-  __device__ __forceinline__ uint32_t a_addr(int chunk, int kg) const {  // 16-byte group kg (0..7) of this row
-    const int s = chunk % TC_STAGES;
-    return smem_u32(tiles + (size_t)s * TC_STAGE_BYTES) + r * 128 + ((kg ^ (r & 7)) << 4);
-  }
-  // The stages of GEMM g's centre chunks are free once the chunk TC_STAGES before the last of them has been
-  // multiplied; the MMA warp signals exactly that on ctr[g & 1] (chunk flag bit 4).  The ring's own `empty`
-  // barriers cannot be used here: this role touches a stage only every few phases, and an mbarrier wait can tell
-  // the current phase from the previous one only.
-  __device__ __forceinline__ void acquire(int g) const { mbar_wait(&sm->ctr[g & 1], (uint32_t)(g >> 1) & 1u); }
-  __device__ __forceinline__ void publish(int first, int count) const {
-    fence_proxy_async();
-    __syncwarp();
-    if ((threadIdx.x & 31) < 8)
-      for (int c = first; c < first + count; ++c) mbar_arrive(&sm->full[c % TC_STAGES]);
-  }
-  __device__ __forceinline__ void sts16(int first, int kgg, uint4 v) const {  // kgg = group index over the GEMM's centre K
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_addr(first + (kgg >> 3), kgg & 7)), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w)
-                 : "memory");
-  }
-  // One 16-channel piece j (channels 16j..16j+15) of a finished tensor: cache write + centre operand of the next GEMM.
-  __device__ __forceinline__ void emit16(int form, int first, int j, const float* x, int tensor, bool raw) const {
-    uint4 p0, p1, n0, n1, r0, r1;
-    {
-      float p[16], n[16];
+// Whole warp: returns once every tile of the previous level has published progress >= need; returns the smallest
+// progress seen (so the caller can skip later polls).  A wait of ~1 s trips the same watchdog as the mbarriers.
+__device__ __noinline__ unsigned int wait_progress(const unsigned int* prog, int first, int count, unsigned int need) {
+  const int lane = threadIdx.x & 31;
+  const long long t0 = clock64();
+  for (unsigned int spins = 0;; ++spins) {
+    unsigned int v = 0xffffffffu;
+    for (int t = first + lane; t < first + count; t += 32) v = min(v, ld_acquire_gpu(prog + t));
 #pragma unroll
-      for (int i = 0; i < 16; ++i) celu(x[i], p[i], n[i]);
-      p0 = make_uint4(pack_h2(p[0], p[1]), pack_h2(p[2], p[3]), pack_h2(p[4], p[5]), pack_h2(p[6], p[7]));
-      p1 = make_uint4(pack_h2(p[8], p[9]), pack_h2(p[10], p[11]), pack_h2(p[12], p[13]), pack_h2(p[14], p[15]));
-      n0 = make_uint4(pack_h2(n[0], n[1]), pack_h2(n[2], n[3]), pack_h2(n[4], n[5]), pack_h2(n[6], n[7]));
-      n1 = make_uint4(pack_h2(n[8], n[9]), pack_h2(n[10], n[11]), pack_h2(n[12], n[13]), pack_h2(n[14], n[15]));
-      r0 = make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
-      r1 = make_uint4(pack_h2(x[8], x[9]), pack_h2(x[10], x[11]), pack_h2(x[12], x[13]), pack_h2(x[14], x[15]));
-    }
-    if (valid) {
-      uint4* g = reinterpret_cast<uint4*>(actrow + (size_t)tensor * LMT_CELLS * LMT_ACT);
-      g[2 * j] = p0;
-      g[2 * j + 1] = p1;
-      g[10 + 2 * j] = n0;
-      g[10 + 2 * j + 1] = n1;
-      if (raw) {
-        g[20 + 2 * j] = r0;
-        g[20 + 2 * j + 1] = r1;
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (v >= need) return v;
+    if ((spins & 63u) == 63u) {
+      if (*(volatile unsigned int*)&g_wedge[0]) return 0xffffffffu;
+      if (clock64() - t0 > 2000000000ll) {
+        if (lane == 0 && atomicCAS(&g_wedge[0], 0u, 1u) == 0u) {
+          g_wedge[1] = blockIdx.x;
+          g_wedge[2] = threadIdx.x;
+          g_wedge[3] = 0xffffffffu;
+          g_wedge[4] = need;
+          __threadfence();
+        }
+        return 0xffffffffu;
       }
     }
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    if (form == FORM_PAIR) {  // K = [elu(x) 0..79 | elu(-x) 80..159 | 0 .. 191]
-      sts16(first, 2 * j, p0);
-      sts16(first, 2 * j + 1, p1);
-      sts16(first, 10 + 2 * j, n0);
-      sts16(first, 10 + 2 * j + 1, n1);
-      if (j < 4) sts16(first, 20 + j, z);
+    __nanosleep(64);
+  }
+}
+
+// 16-byte group kg (0..7) of row r of the A tile in the ring stage of schedule chunk `chunk` (128-byte swizzle)
+__device__ __forceinline__ void sts_a(unsigned char* tiles, int stage, int stage_bytes, int kg, int r, uint4 v) {
+  const uint32_t addr = smem_u32(tiles + (size_t)stage * stage_bytes) + r * 128 + ((kg ^ (r & 7)) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct Epi {
+  TcSmem* sm;
+  uint32_t tlane;   // TMEM address of this thread's lane, column 0
+  bool valid;
+  int dbg;
+  __half* actrow;  // act + (b * 33 * 1024 + cell) * 240; tensor t adds t * 1024 * 240
+
+  // the centre operand of the next GEMM is complete in TMEM: one arrival per epilogue warp
+  __device__ __forceinline__ void publish() const {
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&sm->cfull);
+  }
+  // the cache rows of one more tensor have been written by this warp
+  __device__ __forceinline__ void step_done() const {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) red_release_cta_shared_inc(&sm->step_count);
+  }
+  // One 16-channel piece j (channels 16j..16j+15) of a finished tensor: cache write + centre operand of the next GEMM.
+  __device__ __forceinline__ void emit16(int form, int j, const float* x, int tensor, bool raw) const {
+    uint32_t pp[8], nn[8], rr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float p0, n0, p1, n1;
+      if (dbg & 8) {
+        p0 = n0 = x[2 * i];
+        p1 = n1 = x[2 * i + 1];
+      } else {
+        celu(x[2 * i], p0, n0);
+        celu(x[2 * i + 1], p1, n1);
+      }
+      pp[i] = pack_h2(p0, p1);
+      nn[i] = pack_h2(n0, n1);
+      rr[i] = pack_h2(x[2 * i], x[2 * i + 1]);
+    }
+    if (form == FORM_PAIR) {  // K = [elu(x) 0..79 | elu(-x) 80..159 | 0 .. 191]: two fp16 per TMEM column
+      tmem_st8_nowait(tlane + COL_A + 8 * j, pp);
+      tmem_st8_nowait(tlane + COL_A + 40 + 8 * j, nn);
     } else if (form == FORM_RAW) {  // K = [x 0..79 | 0 .. 127]
-      sts16(first, 2 * j, r0);
-      sts16(first, 2 * j + 1, r1);
-      sts16(first, 10 + j, z);
-      if (j == 0) sts16(first, 15, z);
+      const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      tmem_st8_nowait(tlane + COL_A + 8 * j, rr);
+      if (j < 3) tmem_st8_nowait(tlane + COL_A + 40 + 8 * j, z);
+    }
+    if (valid && !(dbg & 4)) {
+      uint4* g = reinterpret_cast<uint4*>(actrow + (size_t)tensor * LMT_CELLS * LMT_ACT);
+      g[2 * j] = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+      g[2 * j + 1] = make_uint4(pp[4], pp[5], pp[6], pp[7]);
+      g[10 + 2 * j] = make_uint4(nn[0], nn[1], nn[2], nn[3]);
+      g[10 + 2 * j + 1] = make_uint4(nn[4], nn[5], nn[6], nn[7]);
+      if (raw) {
+        g[20 + 2 * j] = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+        g[20 + 2 * j + 1] = make_uint4(rr[4], rr[5], rr[6], rr[7]);
+      }
     }
   }
 };
@@ -247,7 +325,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   // the shuffle tells the compiler the warp index is warp-uniform: role branches become uniform branches and the
   // issuing roles' descriptor arithmetic can stay in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int row0 = p.row_begin + blockIdx.x * p.rows_per_cta;
+
+  // tiles are handed out in level order: whatever this tile waits for is already running or finished
+  if (tid == 0) {
+    const int t = (int)atomicAdd(p.sync, 1u);
+    sm.tile_index = t;
+    sm.tile = p.tiles[t];
+    sm.step_count = 0;
+  }
+  for (int i = tid; i < p.n_total; i += TC_THREADS) sm.sched[i] = pack_chunk(p.chunks[i]);
+  __syncthreads();
+  const Tile tile = sm.tile;
+  const int tile_index = sm.tile_index;
+  const bool traced = tile_index == p.n_tiles - 1;
+  const unsigned int* prog = p.sync + 16;
+  // Ring geometry: the A tile of a stage holds only the tile's rows (rounded up to 8); the MMA still reads 128 rows
+  // and runs on into the stage's weight tile, which only feeds accumulator lanes nobody looks at.
+  const int a_rows = (tile.nrows + 7) & ~7;
+  const int a_bytes = a_rows * 128;
+  const int stage_bytes = a_bytes + TC_W_BYTES;
+  const int nst = min(TC_MAX_STAGES, (TC_STAGES * TC_STAGE_BYTES) / stage_bytes);
 
   if (tid < 128) {
     ps_lmconv_row ri;
@@ -255,18 +352,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     ri.w01 = 0;
     ri.w2_flags = 0;
     ri.uidx = 0;
-    if (tid < p.rows_per_cta && row0 + tid < p.row_end) ri = p.rows[row0 + tid];
+    if (tid < tile.nrows) ri = p.rows[tile.row_begin + tid];
     sm.rows[tid] = ri;
   }
-  for (int i = tid; i < p.n_total; i += TC_THREADS) sm.sched[i] = pack_chunk(p.chunks[i]);
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < TC_STAGES; ++s) {
-        mbar_init(&sm.full[s], 33);  // 32 arrivals of the row writers (one gather warp, or 8 lanes of each epilogue warp) + the weight producer
+      for (int s = 0; s < nst; ++s) {
+        mbar_init(&sm.full[s], 33);  // 32 arrivals of the row writers (a gather warp, or the weight producer's lanes for an operand that is not in the ring) + the weight copy
         mbar_init(&sm.empty[s], 1);
       }
       for (int i = 0; i < 3; ++i) mbar_init(&sm.acc_full[i], 1);
-      for (int i = 0; i < 2; ++i) mbar_init(&sm.ctr[i], 1);
+      mbar_init(&sm.cfull, 4);
       mbar_fence_init();
     }
     __syncwarp();
@@ -274,64 +370,86 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   }
   tc_fence_before();
   const int need_logits =
-      __syncthreads_or(tid < p.rows_per_cta && row0 + tid < p.row_end &&
-                       (p.rows[row0 + tid].w2_flags & (ROW_SAMPLED | ROW_LOGITS)));
+      __syncthreads_or(tid < tile.nrows && (p.rows[tile.row_begin + tid].w2_flags & (ROW_SAMPLED | ROW_LOGITS)));
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, sm.tmem_slot, 0);
   if (tid == 0) TC_TRACE(7, 0);
-#ifdef PS_TC_DEBUG
-  if (tid == 0 && blockIdx.x == 0) printf("lmconv_tc: full[0] at smem 0x%x, rows %d..%d need_logits %d\n", smem_u32(&sm.full[0]), p.row_begin, p.row_end, need_logits);
-#endif
   const int nchunks = need_logits ? p.n_total : p.n_body;
 
   if (warp == 0) {
     // ===== weight producer: whole warp, warp-uniform values, one elected lane issues (see umma_f16_kblock) =====
-    {
-      int s = 0;
-      uint32_t ph = 1;
-      for (int i = 0; i < nchunks; ++i) {
-        uint2 raw = sm.sched[i];
-        raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
-        mbar_wait(&sm.empty[s], ph);
-        if (lane == 0) TC_TRACE(3, i);
-        const uint32_t bytes = ((raw.x >> 24) & 31u) << 10;  // w_rows * 128
-        if (p.debug & 1) {
-          if (lane == 0) mbar_arrive(&sm.full[s]);
-        } else {
-          bulk_load_elect(tiles + (size_t)s * TC_STAGE_BYTES + TC_A_BYTES, p.wblob + (size_t)(raw.x & 0xffffffu) * 16, bytes,
-                          &sm.full[s]);
-        }
-        if (++s == TC_STAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
+    int s = 0;
+    uint32_t ph = 1;
+    for (int i = 0; i < nchunks; ++i) {
+      uint2 raw = sm.sched[i];
+      raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
+      mbar_wait(&sm.empty[s], ph);
+      if (lane == 0) TC_TRACE(3, i);
+      const uint32_t bytes = ((raw.x >> 24) & 31u) << 10;  // w_rows * 128
+      const uint32_t kind = raw.x >> 29;
+      if (kind == A_TMEM || kind == A_REUSE) mbar_arrive(&sm.full[s]);  // nobody writes rows into this stage
+      if (p.debug & 1) {
+        if (lane == 0) mbar_arrive(&sm.full[s]);
+      } else {
+        bulk_load_elect(tiles + (size_t)s * stage_bytes + a_bytes, p.wblob + (size_t)(raw.x & 0xffffffu) * 16, bytes,
+                        &sm.full[s]);
+      }
+      if (++s == nst) {
+        s = 0;
+        ph ^= 1u;
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop with warp-uniform values; one elected lane issues =====
-    {
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
-      const uint32_t idesc0 = umma_idesc_f16(0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < nchunks; ++i) {
-        uint2 raw = sm.sched[i];
-        raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
-        raw.y = __shfl_sync(0xffffffffu, raw.y, 0);
-        mbar_wait(&sm.full[s], ph);
-        if (!(p.debug & 8)) fence_proxy_async();
-        tc_fence_after();
-        if (lane == 0) TC_TRACE(0, i);
-        const uint32_t flags = raw.y >> 20;
-        const uint32_t idesc = idesc0 | (((raw.x >> 24) & 31u) << 17);       // N >> 3 = w_rows / 8
-        const uint32_t d = tmem_base + (((raw.y >> 15) & 31u) << 4);          // d_col
-        const uint32_t a_lo = a_lo0 + (uint32_t)s * (TC_STAGE_BYTES >> 4);
-        umma_f16_kblock(d, a_lo, a_lo + (TC_A_BYTES >> 4), idesc, flags & 1u, &sm.empty[s]);
-        if (flags & 2u) umma_commit_elect(&sm.acc_full[(flags >> 2) & 3u]);
-        if (flags & 16u) umma_commit_elect(&sm.ctr[(flags >> 5) & 1u]);
-        if (++s == TC_STAGES) {
-          s = 0;
-          ph ^= 1u;
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
+    const uint32_t idesc0 = umma_idesc_f16(0);
+    int s = 0;
+    uint32_t ph = 0, cph = 0;
+    for (int i = 0; i < nchunks; ++i) {
+      uint2 raw = sm.sched[i];
+      raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
+      raw.y = __shfl_sync(0xffffffffu, raw.y, 0);
+      const uint32_t flags = (raw.y >> 20) & 63u;
+      const uint32_t kind = raw.x >> 29;
+      mbar_wait(&sm.full[s], ph);
+      if (flags & 16u) {  // first centre chunk of a GEMM: the previous epilogue has finished the operand in TMEM
+        mbar_wait(&sm.cfull, cph);
+        cph ^= 1u;
+      }
+      fence_proxy_async();
+      tc_fence_after();
+      if (lane == 0) TC_TRACE(0, i);
+      const uint32_t idesc = idesc0 | (((raw.x >> 24) & 31u) << 17);       // N >> 3 = w_rows / 8
+      const uint32_t d = tmem_base + (((raw.y >> 15) & 31u) << 4);          // d_col
+      const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(a_bytes >> 4);
+      const uint32_t kc = (raw.y >> 9) & 31u;
+      if (kind == A_TMEM) {
+        umma_f16_ts_kblock(d, tmem_base + COL_A + kc * 32u, b_lo, idesc, flags & 1u, &sm.empty[s]);
+      } else {
+        // A_REUSE: the operand the epilogue wrote for nin_out's first quarter stays in that quarter's stages
+        const uint32_t sa = kind == A_REUSE ? (uint32_t)((p.logit_first + (int)kc) % nst) : (uint32_t)s;
+        umma_f16_kblock(d, a_lo0 + sa * (uint32_t)(stage_bytes >> 4), b_lo, idesc, flags & 1u, &sm.empty[s]);
+      }
+      if (flags & 2u) umma_commit_elect(&sm.acc_full[(flags >> 2) & 3u]);
+      if (++s == nst) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  } else if (warp == 10) {
+    // ===== progress publisher: the epilogue warps count finished cache tensors in shared memory; this warp makes
+    // them visible device-wide (the fence is cumulative over what it observed) and moves the tile's progress word =====
+    if (lane == 0) {
+      unsigned int* mine = p.sync + 16 + tile_index;
+      unsigned int published = 0;
+      while (published < PROG_DONE) {
+        const unsigned int done = ld_acquire_cta_shared(&sm.step_count) >> 2;  // four epilogue warps per step
+        if (done > published) {
+          __threadfence();
+          st_release_gpu(mine, done);
+          published = done;
+        } else {
+          __nanosleep(32);
         }
       }
     }
@@ -358,13 +476,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     const int gw = warp - 6, g = lane & 7, rs = lane >> 3;
     const uint32_t dst_even = smem_u32(tiles) + rs * 128 + ((g ^ rs) << 4);        // rows rs + 8m
     const uint32_t dst_odd = smem_u32(tiles) + (rs + 4) * 128 + ((g ^ (rs + 4)) << 4);  // rows rs + 4 + 8m
-    const int npair = p.rows_per_cta >> 3;  // row pairs (rs + 8m, rs + 4 + 8m) of this lane
-    int seen = 0;                            // gathered chunks so far: this warp takes those with seen % 4 == gw
+    const int npair = (tile.nrows + 7) >> 3;  // row pairs (rs + 8m, rs + 4 + 8m) of this lane
+    int seen = 0;                              // gathered chunks so far: this warp takes those with seen % 4 == gw
+    unsigned int verified = tile.prev_count ? 0u : 0xffffffffu;  // progress every earlier level is known to have reached
+    if (verified < (unsigned int)tile.wait_start)
+      verified = wait_progress(prog, tile.prev_first, tile.prev_count, (unsigned int)tile.wait_start);
     for (int i = 0; i < nchunks; ++i) {
       const Chunk ch = unpack_chunk(sm.sched[i]);
-      if (ch.a_kind == A_EPILOGUE) continue;
+      if (ch.a_kind != A_GATHER && ch.a_kind != A_CENTRE) continue;
       if ((seen++ & 3) != gw) continue;
-      const int s = i % TC_STAGES;
+      const int s = i % nst;
       const int kg = ch.kc * 8 + g;
       int bitpos, off;  // mask bit to test, byte offset from the row's base
       if (ch.a_kind == A_GATHER) {
@@ -375,13 +496,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         const int dil = ch.mask == 2 ? 2 : 1;
         bitpos = ch.mask * 9 + tap;
         off = (((tr - 1) * 32 + (tap - 3 * tr - 1)) * dil + ch.a_tensor * LMT_CELLS) * (LMT_ACT * 2) + (ch.ch_off8 + c8) * 16;
+        // GEMM j reads tensors the neighbours wrote at step <= j.  Waiting until the previous level is a step further
+        // (progress >= j + 2) also proves, by induction over the levels, that every earlier level has reached j + 1.
+        const unsigned int need = (unsigned int)min(ch.gemm + 2, LMT_TENSORS);
+        if (verified < need) verified = wait_progress(prog, tile.prev_first, tile.prev_count, need);
       } else {
         bitpos = kg < ch.cin8 ? 27 : 31;
         off = ch.a_tensor * LMT_CELLS * (LMT_ACT * 2) + (ch.ch_off8 + kg) * 16;
       }
-      mbar_wait(&sm.empty[s], ((uint32_t)(i / TC_STAGES) & 1u) ^ 1u);
+      mbar_wait(&sm.empty[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
       if (lane == 0) TC_TRACE(1, i);
-      const uint32_t soff = s * TC_STAGE_BYTES;
+      const uint32_t soff = s * stage_bytes;
       if (!(p.debug & 2)) {
 #pragma unroll 4
         for (int m = 0; m < npair; ++m) {
@@ -396,26 +521,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       // asynchronous completion: the stage's full barrier gets this lane's arrival when its copies have landed, so
       // the warp never blocks on data and every free stage of the ring is in flight (the MMA warp orders the
       // landed generic-proxy writes before its async-proxy reads with fence.proxy.async)
-      if (p.debug & 32)
-        mbar_arrive(&sm.full[s]);  // timing experiment (with bit 1): how long does the asynchronous arrival itself take?
-      else
-        cp_async_arrive_noinc(&sm.full[s]);
+      cp_async_arrive_noinc(&sm.full[s]);
       if (lane == 0) TC_TRACE(2, i);
     }
   } else {
     // ===== epilogue: one thread per row =====
     Epi e;
-    e.tiles = tiles;
     e.sm = &sm;
+    e.dbg = p.debug;
     const int quad = warp & 3;
-    e.r = quad * 32 + lane;
+    const int r = quad * 32 + lane;
     e.tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const ps_lmconv_row ri = sm.rows[e.r];
+    const ps_lmconv_row ri = sm.rows[r];
     e.valid = (ri.w2_flags & ROW_VALID) != 0;
     const int b = ri.bc >> 10, cell = ri.bc & 1023;
     e.actrow = p.act + ((size_t)b * LMT_TENSORS * LMT_CELLS + cell) * LMT_ACT;
     const float* bias = p.bias;
     int g = 0;  // GEMM counter
+
+    // the first layer reads the neighbours' tokens: a level with sampled cells starts when the previous one has drawn
+    if (tile.wait_start && tile.prev_count)
+      wait_progress(prog, tile.prev_first, tile.prev_count, (unsigned int)tile.wait_start);
 
     // ---- u_init over [one-hot(code) | ones]: a gather of weight rows (mask A), then PONO ----
     {
@@ -427,7 +553,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       for (int tap = 0; tap < 9; ++tap) {
         if (!((w0 >> tap) & 1u)) continue;
         const int nbr = cell + (tap / 3 - 1) * 32 + (tap % 3 - 1);
-        const int code = (int)p.codes[(size_t)b * LMT_CELLS + nbr];
+        const int code = (int)__ldcg(p.codes + (size_t)b * LMT_CELLS + nbr);  // written by other SMs in this launch
         const uint4* wc = reinterpret_cast<const uint4*>(p.w_uinit + ((size_t)tap * (LMT_CLASSES + 1) + code) * LMT_F);
         const uint4* w1 = reinterpret_cast<const uint4*>(p.w_uinit + ((size_t)tap * (LMT_CLASSES + 1) + LMT_CLASSES) * LMT_F);
 #pragma unroll
@@ -444,26 +570,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         }
       }
       pono80(v);
-      const int first = p.epi_first[0];
-      e.acquire(0);
+      {  // K columns 160..191 of the centre operand stay zero for the whole tile
+        const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        tmem_st8_nowait(e.tlane + COL_A + 80, z);
+        tmem_st8_nowait(e.tlane + COL_A + 88, z);
+      }
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
         tmem_st16_nowait(e.tlane + COL_OG + 16 * j, v + 16 * j);
-        e.emit16(FORM_PAIR, first, j, v + 16 * j, 0, true);
+        e.emit16(FORM_PAIR, j, v + 16 * j, 0, (p.raw_mask >> 0) & 1ull);
       }
-      tmem_st_wait();
-      e.publish(first, 3);
+      e.publish();
+      e.step_done();
     }
 
     for (int oi = 0; oi < TC_NOPS; ++oi) {
       const ps_lmconv_op op = p.ops[oi];
       const int next_form = oi + 1 < TC_NOPS ? (p.ops[oi + 1].kind == 0 ? FORM_PAIR : FORM_RAW) : FORM_NONE;
-      const int next_count = next_form == FORM_PAIR ? 3 : (next_form == FORM_RAW ? 2 : 0);
+      const bool out_raw = (p.raw_mask >> op.out) & 1ull;
       if (op.kind == 0) {
         {  // x = PONO(conv_input(concat_elu(og))) [+ nin_skip(concat_elu(a))]
           const uint32_t col0 = (uint32_t)(g & 1) * 160u;
           mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
-          if (e.r == 0) TC_TRACE(4, g);
+          if (r == 0) TC_TRACE(4, g);
           tc_fence_after();
           float x[LMT_F];
 #pragma unroll
@@ -482,20 +611,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
               for (int i = 0; i < 16; ++i) x[16 * j + i] += sk[i];
             }
           }
-          tc_fence_before();
-          const int first = p.epi_first[g + 1];
-          e.acquire(g + 1);
-          if (e.r == 0) TC_TRACE(6, g);
+          if (r == 0) TC_TRACE(6, g);
 #pragma unroll
-          for (int j = 0; j < 5; ++j) e.emit16(FORM_PAIR, first, j, x + 16 * j, op.mid, false);
-          e.publish(first, 3);
-          if (e.r == 0) TC_TRACE(5, g);
+          for (int j = 0; j < 5; ++j) e.emit16(FORM_PAIR, j, x + 16 * j, op.mid, false);
+          e.publish();
+          e.step_done();
+          if (r == 0) TC_TRACE(5, g);
           ++g;
         }
         {  // y = conv_out(concat_elu(x)); og += PONO(y[:80]) * sigmoid(y[80:])
           const uint32_t col0 = (uint32_t)(g & 1) * 160u;
           mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
-          if (e.r == 0) TC_TRACE(4, g);
+          if (r == 0) TC_TRACE(4, g);
           tc_fence_after();
           float a[LMT_F];
 #pragma unroll
@@ -503,8 +630,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
           tmem_ld_wait();
           add_bias80(a, bias + op.b_out);
           pono80(a);
-          const int first = next_count ? p.epi_first[g + 1] : 0;
-          if (next_count) e.acquire(g + 1);
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
             float gt[16], o[16];
@@ -513,20 +638,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
             tmem_ld_wait();
             add_bias16(gt, bias + op.b_out + 80 + 16 * j);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = fmaf(a[16 * j + i], 1.0f / (1.0f + __expf(-gt[i])), o[i]);
+            for (int i = 0; i < 16; ++i) o[i] = fmaf(a[16 * j + i], __fdividef(1.0f, 1.0f + __expf(-gt[i])), o[i]);
             tmem_st16_nowait(e.tlane + COL_OG + 16 * j, o);
-            e.emit16(next_form, first, j, o, op.out, true);
+            e.emit16(next_form, j, o, op.out, out_raw);
           }
-          tmem_st_wait();
-          tc_fence_before();
-          e.publish(first, next_count);
-          if (e.r == 0) TC_TRACE(5, g);
+          if (next_form != FORM_NONE) e.publish(); else { tmem_st_wait(); tc_fence_before(); }
+          e.step_done();
+          if (r == 0) TC_TRACE(5, g);
           ++g;
         }
       } else {  // dilated masked conv on the raw stream + PONO becomes the new stream
         const uint32_t col0 = (uint32_t)(g & 1) * 160u;
         mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
-        if (e.r == 0) TC_TRACE(4, g);
+        if (r == 0) TC_TRACE(4, g);
         tc_fence_after();
         float x[LMT_F];
 #pragma unroll
@@ -534,28 +658,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         tmem_ld_wait();
         add_bias80(x, bias + op.b_in);
         pono80(x);
-        const int first = next_count ? p.epi_first[g + 1] : 0;
-        if (next_count) e.acquire(g + 1);
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
           tmem_st16_nowait(e.tlane + COL_OG + 16 * j, x + 16 * j);
-          e.emit16(next_form, first, j, x + 16 * j, op.out, true);
+          e.emit16(next_form, j, x + 16 * j, op.out, out_raw);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        e.publish(first, next_count);
-        if (e.r == 0) TC_TRACE(5, g);
+        if (next_form != FORM_NONE) e.publish(); else { tmem_st_wait(); tc_fence_before(); }
+        e.step_done();
+        if (r == 0) TC_TRACE(5, g);
         ++g;
       }
     }
 
     if (need_logits) {
-      // ---- logits = nin_out(elu(u)): four 128-class quarters, A = elu(u) rewritten per quarter ----
-      for (int q = 0; q < 4; ++q) {
-        const int first = p.epi_first[g + q];
-        // quarters 0-2 reuse stages whose last users (body chunks) completed before acc_full of the last GEMM fired;
-        // quarter 3 reuses quarter 0's stages: the schedule signals that on ctr as if it were GEMM g + 1
-        if (q == 3) e.acquire(g + 1);
+      // ---- logits = nin_out(elu(u)): four 128-class quarters share one operand A = [elu(u) | 0], written into
+      // the ring stages of quarter 0's two chunks.  Their last users (body chunks) completed before the last
+      // accumulator barrier fired, and no later chunk writes rows into them. ----
+      {
+        const int first = p.logit_first;
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
           float o[16], pp[16], nn;
@@ -563,16 +683,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) celu(o[i], pp[i], nn);
-          e.sts16(first, 2 * j,
+          if (r < a_rows) {  // rows past the tile's A tile would land in the stage's weights
+            const int kg0 = 2 * j, kg1 = 2 * j + 1;
+            sts_a(tiles, (first + (kg0 >> 3)) % nst, stage_bytes, kg0 & 7, r,
                   make_uint4(pack_h2(pp[0], pp[1]), pack_h2(pp[2], pp[3]), pack_h2(pp[4], pp[5]), pack_h2(pp[6], pp[7])));
-          e.sts16(first, 2 * j + 1,
-                  make_uint4(pack_h2(pp[8], pp[9]), pack_h2(pp[10], pp[11]), pack_h2(pp[12], pp[13]),
-                             pack_h2(pp[14], pp[15])));
-          e.sts16(first, 10 + j, make_uint4(0, 0, 0, 0));
-          if (j == 0) e.sts16(first, 15, make_uint4(0, 0, 0, 0));
+            sts_a(tiles, (first + (kg1 >> 3)) % nst, stage_bytes, kg1 & 7, r,
+                  make_uint4(pack_h2(pp[8], pp[9]), pack_h2(pp[10], pp[11]), pack_h2(pp[12], pp[13]), pack_h2(pp[14], pp[15])));
+            sts_a(tiles, (first + 1) % nst, stage_bytes, 2 + j, r, make_uint4(0, 0, 0, 0));
+            if (j == 0) sts_a(tiles, (first + 1) % nst, stage_bytes, 7, r, make_uint4(0, 0, 0, 0));
+          }
         }
         tc_fence_before();
-        e.publish(first, 2);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane < 8) {
+          mbar_arrive(&sm.full[first % nst]);
+          mbar_arrive(&sm.full[(first + 1) % nst]);
+        }
       }
       mbar_wait(&sm.acc_full[2], 0);
       tc_fence_after();
@@ -620,10 +747,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
             }
           }
         }
-        if (sampled) p.codes[(size_t)b * LMT_CELLS + cell] = token;
+        if (sampled) __stcg(p.codes + (size_t)b * LMT_CELLS + cell, (long long)token);
       }
       tc_fence_before();
     }
+    e.step_done();  // progress PROG_DONE: the tile's tokens (if any) are in `codes`
   }
   __syncthreads();
   if (tid == 0) TC_TRACE(7, 1);
@@ -641,21 +769,30 @@ extern "C" {
 // developer aid (tools/trace_lmconv.py): device buffer of 8 x 1024 int64 receiving CTA 0's timestamps, or NULL
 void ps_lmconv_tc_set_trace(void* dev_buffer) { g_tc_trace = (long long*)dev_buffer; }
 
+// activation cache + the launch's tile table and progress words
+static size_t tc_act_bytes(int B) { return (size_t)(B > 0 ? B : 0) * LMT_TENSORS * LMT_CELLS * LMT_ACT * sizeof(__half); }
+static size_t tc_max_tiles(int B) { return (size_t)(B > 0 ? B : 0) * LMT_CELLS + 1; }
 size_t ps_lmconv_tc_cache_bytes(int B) {
-  return (size_t)(B > 0 ? B : 0) * LMT_TENSORS * LMT_CELLS * LMT_ACT * sizeof(__half);
+  return align_up(tc_act_bytes(B), 256) + align_up(tc_max_tiles(B) * sizeof(Tile), 256) + (tc_max_tiles(B) + 16) * sizeof(unsigned int);
 }
 
-// Levels of the dependency DAG (host): a cell sits one level above the highest of its masked-in neighbours (the first
-// cell of the order, which reads nothing, is level 0).  mode 0: sampling -- cells ranked after the image's last
-// sampled cell are dropped, images with nothing to sample produce no rows.  mode 1: teacher-forced logits of every
-// cell.
+// Dependency levels (host).  A cell reads, through its three masks, cells generated earlier; it sits one level above
+// the highest of them.  Rows come out in two phases:
+//   phase A  the known prefix: cells that neither are sampled nor have a sampled cell among their ancestors.  Their
+//            tokens are all known, so consecutive levels can run as a pipeline a layer apart;
+//   phase B  sampled cells and everything downstream of one, levelled among themselves (a B cell's A neighbours are
+//            complete before phase B starts).  A B level needs the previous level's tokens before its first layer.
+// level_offsets lists the A levels then the B levels; *first_b_level is the index of the first B level (== *n_levels
+// when there is none).  mode 0: sampling -- cells ranked after the image's last sampled cell are dropped, images with
+// nothing to sample produce no rows.  mode 1: teacher-forced logits of every cell (all phase A).
 int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t* sample_mask, int B, int mode,
-                          ps_lmconv_row* rows_out, int* level_offsets, int max_levels, int* n_levels) {
-  PS_CHECK_ARG(order && words && rows_out && level_offsets && n_levels && B >= 0 && max_levels >= 2);
+                          ps_lmconv_row* rows_out, int* level_offsets, int max_levels, int* n_levels, int* first_b_level) {
+  PS_CHECK_ARG(order && words && rows_out && level_offsets && n_levels && first_b_level && B >= 0 && max_levels >= 2);
   PS_CHECK_ARG(mode == 1 || sample_mask);
   PS_CHECK_ARG(B < (1 << 20));
+  // level >= 0: phase A level; level <= -2: phase B level -(level + 2); -1: no row
   std::vector<int> level((size_t)B * LMT_CELLS, -1), uidx((size_t)B * LMT_CELLS, 0), rank(LMT_CELLS);
-  int top = 0;
+  int top_a = -1, top_b = -1;
   for (int b = 0; b < B; ++b) {
     const int* ord = order + (size_t)b * LMT_CELLS;
     const uint16_t* w = words + (size_t)b * 3 * LMT_CELLS;
@@ -665,8 +802,8 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
       rank[ord[i]] = i;
     }
     int last = LMT_CELLS - 1;
+    const uint8_t* smk = mode == 0 ? sample_mask + (size_t)b * LMT_CELLS : nullptr;
     if (mode == 0) {
-      const uint8_t* smk = sample_mask + (size_t)b * LMT_CELLS;
       int drawn = 0;
       last = -1;
       for (int i = 0; i < LMT_CELLS; ++i)
@@ -679,7 +816,8 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
     for (int i = 0; i <= last; ++i) {
       const int cell = ord[i];
       const int r = cell / 32, c = cell % 32;
-      int l = -1;
+      int la = -1, lb = -1;
+      bool in_b = smk && smk[cell];
       for (int m = 0; m < 3; ++m) {
         const int dil = m == 2 ? 2 : 1;
         for (int t = 0; t < 9; ++t) {
@@ -687,24 +825,37 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
           const int rr = r + (t / 3 - 1) * dil, cc = c + (t % 3 - 1) * dil;
           PS_CHECK_ARG(rr >= 0 && rr < 32 && cc >= 0 && cc < 32);       // masks never reach outside the grid
           PS_CHECK_ARG(rank[rr * 32 + cc] < i);                          // ... nor forward in the order
-          l = std::max(l, lv[rr * 32 + cc]);
+          const int l = lv[rr * 32 + cc];
+          if (l >= 0) {
+            la = std::max(la, l);
+          } else {
+            in_b = true;
+            lb = std::max(lb, -(l + 2));
+          }
         }
       }
-      lv[cell] = l + 1;
-      top = std::max(top, l + 1);
+      if (in_b) {
+        lv[cell] = -(lb + 1 + 2);
+        top_b = std::max(top_b, lb + 1);
+      } else {
+        lv[cell] = la + 1;
+        top_a = std::max(top_a, la + 1);
+      }
     }
   }
-  if (top + 1 > max_levels) return fail(PS_EWORKSPACE, "%s: more dependency levels than level_offsets holds%s", __func__);
-  std::vector<int> count(top + 2, 0);
+  const int na = top_a + 1, nb = top_b + 1;
+  if (na + nb > max_levels) return fail(PS_EWORKSPACE, "%s: more dependency levels than level_offsets holds%s", __func__);
+  auto slot = [&](int l) { return l >= 0 ? l : na - (l + 2); };
+  std::vector<int> count(na + nb + 1, 0);
   for (size_t i = 0; i < level.size(); ++i)
-    if (level[i] >= 0) ++count[level[i] + 1];
-  for (int l = 0; l <= top; ++l) count[l + 1] += count[l];
-  for (int l = 0; l <= top + 1; ++l) level_offsets[l] = count[l];
+    if (level[i] != -1) ++count[slot(level[i]) + 1];
+  for (int l = 0; l < na + nb; ++l) count[l + 1] += count[l];
+  for (int l = 0; l <= na + nb; ++l) level_offsets[l] = count[l];
   std::vector<int> cursor(count.begin(), count.end() - 1);
   for (int b = 0; b < B; ++b)
     for (int cell = 0; cell < LMT_CELLS; ++cell) {
       const int l = level[(size_t)b * LMT_CELLS + cell];
-      if (l < 0) continue;
+      if (l == -1) continue;
       const uint16_t* w = words + (size_t)b * 3 * LMT_CELLS;
       ps_lmconv_row ri;
       ri.bc = (b << 10) | cell;
@@ -715,21 +866,22 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
       else if (sample_mask[(size_t)b * LMT_CELLS + cell])
         ri.w2_flags |= ROW_SAMPLED;
       ri.uidx = uidx[(size_t)b * LMT_CELLS + cell];
-      rows_out[cursor[l]++] = ri;
+      rows_out[cursor[slot(l)]++] = ri;
     }
-  *n_levels = count[top + 1] == 0 ? 0 : top + 1;
+  *n_levels = na + nb;
+  *first_b_level = na;
   return PS_OK;
 }
 
 int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* rows_dev, const int* level_offsets_host,
-                     int n_levels, long long* codes, const float* uniforms, int uniforms_stride, float temperature,
-                     float* logits_out, void* cache, size_t cache_bytes, void* stream) {
+                     int n_levels, int first_b_level, long long* codes, const float* uniforms, int uniforms_stride,
+                     float temperature, float* logits_out, void* cache, size_t cache_bytes, void* stream) {
   PS_CHECK_ARG(plan && plan->wblob && plan->chunks && plan->w_uinit && plan->bias && codes && cache);
   PS_CHECK_ARG(B >= 0 && n_levels >= 0 && temperature > 0.0f);
   PS_CHECK_ARG(plan->n_chunks_body > 0 && plan->n_chunks_total >= plan->n_chunks_body);
   PS_CHECK_ARG(plan->n_chunks_total <= TC_MAX_CHUNKS);
   if (B == 0 || n_levels == 0) return PS_OK;
-  PS_CHECK_ARG(rows_dev && level_offsets_host);
+  PS_CHECK_ARG(rows_dev && level_offsets_host && first_b_level >= 0 && first_b_level <= n_levels);
   PS_CHECK_ARG(uniforms || logits_out);  // sampling needs the uniform numbers
   if (cache_bytes < ps_lmconv_tc_cache_bytes(B)) return fail(PS_EWORKSPACE, "%s: activation cache too small%s", __func__);
   TcParams p;
@@ -738,11 +890,12 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   p.chunks = plan->chunks;
   p.n_body = plan->n_chunks_body;
   p.n_total = plan->n_chunks_total;
-  memcpy(p.epi_first, plan->epi_first, sizeof(p.epi_first));
+  p.logit_first = plan->epi_first[32];
   p.w_uinit = (const __half*)plan->w_uinit;
   p.bias = plan->bias;
   p.b_uinit = plan->b_uinit;
   p.b_nin = plan->b_nin;
+  p.raw_mask = plan->raw_mask;
   memcpy(p.ops, plan->ops, sizeof(p.ops));
   for (int i = 0; i < TC_NOPS; ++i)
     PS_CHECK_ARG(p.ops[i].out >= 0 && p.ops[i].out < LMT_TENSORS && p.ops[i].mid < LMT_TENSORS);
@@ -755,30 +908,62 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   p.logits_out = logits_out;
   p.trace = g_tc_trace;
   p.debug = getenv("PS_TC_DEBUG") ? atoi(getenv("PS_TC_DEBUG")) : 0;
-  const size_t smem_bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcSmem);
-  static thread_local int attr_dev = -1;
-  int dev = 0;
+
+  int dev = 0, sms = 148;
   PS_CUDA(cudaGetDevice(&dev));
+  PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // tiles in level order: a level's rows are split evenly over its tiles
+  std::vector<Tile> tiles;
+  int prev_first = 0, prev_count = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const int r0 = level_offsets_host[l], r1 = level_offsets_host[l + 1];
+    PS_CHECK_ARG(r1 >= r0);
+    if (r1 == r0) continue;
+    // The prefix levels overlap each other, so their tiles are full (fewest SMs per level).  A sampled level runs
+    // alone and its time is one tile's latency: small tiles get a deeper operand ring and there are SMs to spare.
+    int rpt = 128;
+    if (l >= first_b_level) {
+      rpt = 32;
+      while (rpt < 128 && (r1 - r0 + rpt - 1) / rpt > sms) rpt *= 2;
+    }
+    const int nt = (r1 - r0 + rpt - 1) / rpt;
+    const int first = (int)tiles.size();
+    for (int t = 0; t < nt; ++t) {
+      Tile tl;
+      memset(&tl, 0, sizeof(tl));
+      tl.row_begin = r0 + (int)((long long)(r1 - r0) * t / nt);
+      tl.nrows = r0 + (int)((long long)(r1 - r0) * (t + 1) / nt) - tl.row_begin;
+      tl.prev_first = prev_first;
+      tl.prev_count = prev_count;
+      // first B level: the whole prefix must be cached; later B levels: the previous level's tokens must be drawn
+      tl.wait_start = l < first_b_level ? 0 : (l == first_b_level ? LMT_TENSORS : PROG_DONE);
+      tiles.push_back(tl);
+    }
+    prev_first = first;
+    prev_count = nt;
+  }
+  const int n_tiles = (int)tiles.size();
+  if (n_tiles == 0) return PS_OK;
+  PS_CHECK_ARG((size_t)n_tiles <= tc_max_tiles(B));
+  char* tail = (char*)cache + align_up(tc_act_bytes(B), 256);
+  Tile* tiles_dev = (Tile*)tail;
+  unsigned int* sync_dev = (unsigned int*)(tail + align_up(tc_max_tiles(B) * sizeof(Tile), 256));
+  PS_CUDA(cudaMemcpyAsync(tiles_dev, tiles.data(), (size_t)n_tiles * sizeof(Tile), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  PS_CUDA(cudaMemsetAsync(sync_dev, 0, ((size_t)n_tiles + 16) * sizeof(unsigned int), (cudaStream_t)stream));
+  p.tiles = tiles_dev;
+  p.n_tiles = n_tiles;
+  p.sync = sync_dev;
+
+  const size_t smem_bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcSmem);
+  static_assert(1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcSmem) <= 227 * 1024, "shared memory budget");
+  static thread_local int attr_dev = -1;
   if (attr_dev != dev) {
     PS_CUDA(cudaFuncSetAttribute(lmconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr_dev = dev;
   }
-  int sms = 148;
-  PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   PS_TIME_BEGIN("lmconv_tc_kernel", (cudaStream_t)stream);
-  for (int l = 0; l < n_levels; ++l) {
-    const int r0 = level_offsets_host[l], r1 = level_offsets_host[l + 1];
-    if (r1 <= r0) continue;
-    // a level is latency bound per CTA (a 36-GEMM dependent chain), so small levels use fewer rows of each
-    // 128-row tile and more SMs; full tiles once the level fills the GPU
-    int rpc = 32;
-    while (rpc < 128 && (r1 - r0 + rpc - 1) / rpc > sms) rpc *= 2;
-    p.row_begin = r0;
-    p.row_end = r1;
-    p.rows_per_cta = rpc;
-    lmconv_tc_kernel<<<(r1 - r0 + rpc - 1) / rpc, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
-    PS_LAUNCHED();
-  }
+  lmconv_tc_kernel<<<n_tiles, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+  PS_LAUNCHED();
   PS_TIME_END((cudaStream_t)stream);
   if (getenv("PS_CHECK_WEDGE")) {  // developer aid: synchronise and report a wedged barrier protocol
     unsigned int w[8] = {0};

@@ -192,6 +192,35 @@ __device__ __forceinline__ void umma_f16_kblock(uint32_t tmem_d, uint32_t a_lo, 
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128), "r"(smem_u32(commit_bar))
       : "memory");
 }
+// The same K block with the A operand in tensor memory (A-from-TMEM form): the row's 64 K values are 32 consecutive
+// 32-bit columns of its lane (two fp16 per column, even k in the low half), 8 columns per K=16 step.
+__device__ __forceinline__ void umma_f16_ts_kblock(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t acc, uint64_t* commit_bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt;\n\t"
+      ".reg .b64 db;\n\t"
+      ".reg .b32 ta;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b32 ta, %1;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pa;\n\t"
+      "add.u32 ta, ta, 8;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+      "add.u32 ta, ta, 8;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+      "add.u32 ta, ta, 8;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128), "r"(smem_u32(commit_bar))
+      : "memory");
+}
 // whole warp, one elected lane commits
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
@@ -251,6 +280,11 @@ __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const float* f)
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8_nowait(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

@@ -17,9 +17,8 @@ from ._lib import check
 
 U0, DS0, DS1, US0, US1 = 0, 13, 14, 31, 32
 MAX_GEMMS = 40
-MAX_LEVELS = 1025
-STAGES = 6  # PS_LMCONV_STAGES
-A_GATHER, A_CENTRE, A_EPILOGUE = 0, 1, 2
+MAX_LEVELS = 2050
+A_GATHER, A_CENTRE, A_EPILOGUE, A_TMEM, A_REUSE = 0, 1, 2, 3, 4
 
 
 class _Op(ctypes.Structure):
@@ -30,7 +29,7 @@ class _Op(ctypes.Structure):
 class _Chunk(ctypes.Structure):
     _fields_ = [("w_off16", ctypes.c_uint32), ("w_rows", ctypes.c_uint16), ("a_kind", ctypes.c_uint8),
                 ("a_tensor", ctypes.c_uint8), ("mask", ctypes.c_uint8), ("cin8", ctypes.c_uint8), ("kc", ctypes.c_uint8),
-                ("ch_off8", ctypes.c_uint8), ("d_col", ctypes.c_uint16), ("flags", ctypes.c_uint8), ("pad", ctypes.c_uint8)]
+                ("ch_off8", ctypes.c_uint8), ("d_col", ctypes.c_uint16), ("flags", ctypes.c_uint8), ("gemm", ctypes.c_uint8)]
 
 
 class _Row(ctypes.Structure):
@@ -40,7 +39,8 @@ class _Row(ctypes.Structure):
 class _Plan(ctypes.Structure):
     _fields_ = [("wblob", ctypes.c_void_p), ("chunks", ctypes.c_void_p), ("n_chunks_body", ctypes.c_int),
                 ("n_chunks_total", ctypes.c_int), ("epi_first", ctypes.c_int * MAX_GEMMS), ("w_uinit", ctypes.c_void_p),
-                ("bias", ctypes.c_void_p), ("b_uinit", ctypes.c_int), ("b_nin", ctypes.c_int), ("ops", _Op * 18)]
+                ("bias", ctypes.c_void_p), ("b_uinit", ctypes.c_int), ("b_nin", ctypes.c_int), ("ops", _Op * 18),
+                ("raw_mask", ctypes.c_uint64)]
 
 
 assert ctypes.sizeof(_Chunk) == 16 and ctypes.sizeof(_Row) == 16
@@ -91,15 +91,17 @@ class LmconvB200:
             self._bn += t.numel()
             return off
 
-        def add_chunks(tiles, rows, a_kind, tensor, mask, cin8, ch_off8, d_col, first_acc, last_bar=None):
+        def add_chunks(tiles, rows, a_kind, tensor, mask, cin8, ch_off8, d_col, first_acc, last_bar=None, gemm=0):
             """one chunk per tile; accumulate flag off only for the very first chunk when first_acc is False"""
             for kc, tile in enumerate(tiles):
                 c = _Chunk()
                 c.w_off16, c.w_rows, c.a_kind, c.a_tensor, c.mask, c.cin8 = self._woff // 16, rows, a_kind, tensor, mask, cin8
-                c.kc, c.ch_off8, c.d_col = kc, ch_off8, d_col
+                c.kc, c.ch_off8, c.d_col, c.gemm = kc, ch_off8, d_col, gemm
                 c.flags = 1 if (first_acc or kc > 0) else 0
                 if last_bar is not None and kc == len(tiles) - 1:
                     c.flags |= 2 | (last_bar << 2)
+                if a_kind == A_TMEM and kc == 0:
+                    c.flags |= 16   # the issuer waits here for the previous epilogue's operand
                 chunks.append(c)
                 blobs.append(tile)
                 self._woff += tile.size
@@ -115,6 +117,7 @@ class LmconvB200:
             return sd[prefix + "lin_a.weight_g"].float() * v / v.norm(dim=1, keepdim=True), add_b(sd[prefix + "lin_a.bias"])
 
         self.gemm = 0
+        self.raw_mask = 0
 
         def masked_gemm(prefix, src, mask, raw, skip=None):
             """chunks of one masked 3x3 conv reading cached tensor `src`: gathered non-centre taps, [nin_skip of tensor
@@ -122,13 +125,16 @@ class LmconvB200:
             wn, wc, b = conv_mats(prefix)
             cout, cin = wc.shape
             col = (self.gemm & 1) * 160
-            add_chunks(swizzle_tiles(wn), cout, A_GATHER, src, mask, cin // 8, 20 if raw else 0, col, False)
+            add_chunks(swizzle_tiles(wn), cout, A_GATHER, src, mask, cin // 8, 20 if raw else 0, col, False, gemm=self.gemm)
+            if raw:
+                self.raw_mask |= 1 << src
             bskip = -1
             if skip is not None:
                 ws, bskip = nin_mat(skip[1])
-                add_chunks(swizzle_tiles(_pad_k(ws)), 80, A_CENTRE, skip[0], 0, 20, 0, col + 80, False)
+                add_chunks(swizzle_tiles(_pad_k(ws)), 80, A_CENTRE, skip[0], 0, 20, 0, col + 80, False, gemm=self.gemm)
             epi_first.append(len(chunks))
-            add_chunks(swizzle_tiles(_pad_k(wc)), cout, A_EPILOGUE, src, mask, cin // 8, 0, col, True, last_bar=self.gemm & 1)
+            add_chunks(swizzle_tiles(_pad_k(wc)), cout, A_TMEM, src, mask, cin // 8, 0, col, True, last_bar=self.gemm & 1,
+                       gemm=self.gemm)
             self.gemm += 1
             return b, bskip
 
@@ -178,22 +184,13 @@ class LmconvB200:
         wno, self.plan.b_nin = nin_mat("nin_out.")            # (512, 80): four 128-class quarters, K padded to 128
         for q in range(4):
             epi_first.append(len(chunks))
-            add_chunks(swizzle_tiles(_pad_k(wno[128 * q:128 * q + 128])), 128, A_EPILOGUE, 30, 0, 10, 0, 128 * q, False,
-                       last_bar=2 if q == 3 else None)
+            add_chunks(swizzle_tiles(_pad_k(wno[128 * q:128 * q + 128])), 128, A_EPILOGUE if q == 0 else A_REUSE, 30, 0, 10, 0,
+                       128 * q, False, last_bar=2 if q == 3 else None, gemm=32 + q)
         self.plan.n_chunks_total = len(chunks)
+        self.plan.raw_mask = self.raw_mask
         assert len(epi_first) <= MAX_GEMMS
         for i, v in enumerate(epi_first):
             self.plan.epi_first[i] = v
-        # Centre-stage release points (chunk flag bit 4, bit 5 = barrier parity): the stages of GEMM i's centre chunks
-        # are free once the chunk STAGES before the last of them has been multiplied.  nin_out quarters 0-2 reuse
-        # stages of body chunks that completed with the last GEMM; quarter 3 waits for quarter 0 (as "GEMM 33").
-        n_centre = [3 if chunks[v].cin8 == 20 else 2 for v in epi_first]
-        for i, v in enumerate(epi_first):
-            if i in (32, 33, 34):
-                continue
-            c = chunks[v + n_centre[i] - 1 - STAGES]
-            assert v + n_centre[i] - 1 - STAGES >= 0 and not (c.flags & 16)
-            c.flags |= 16 | (((33 if i == 35 else i) & 1) << 5)
         self.wblob = torch.from_numpy(np.concatenate(blobs)).to(device)
         self.chunks = torch.from_numpy(np.frombuffer(b"".join(bytes(c) for c in chunks), dtype=np.uint8).copy()).to(device)
         self.bias = torch.cat(bs).to(device).contiguous()
@@ -204,27 +201,29 @@ class LmconvB200:
 
     @staticmethod
     def levels_host(order, words, sample_mask, mode):
-        """ps_lmconv_levels_host: -> (rows uint8 array of 16-byte records, level offsets list)."""
+        """ps_lmconv_levels_host: -> (rows uint8 array of 16-byte records, level offsets, index of the first level of
+        phase B = sampled cells and their descendants; the levels before it are the known prefix)."""
         order = np.ascontiguousarray(np.asarray(order).reshape(-1, 1024).astype(np.int32))
         B = order.shape[0]
         words = np.ascontiguousarray(np.asarray(words).reshape(B, 3, 1024).astype(np.uint16))
         sm = None if sample_mask is None else np.ascontiguousarray(np.asarray(sample_mask).reshape(B, 1024).astype(np.uint8))
         rows = np.zeros((B * 1024, 16), np.uint8)
         offs = np.zeros(MAX_LEVELS + 1, np.int32)
-        n = ctypes.c_int(0)
+        n, first_b = ctypes.c_int(0), ctypes.c_int(0)
         check(_lib.lib().ps_lmconv_levels_host(order.ctypes.data, words.ctypes.data, None if sm is None else sm.ctypes.data, B,
-                                               int(mode), rows.ctypes.data, offs.ctypes.data, MAX_LEVELS, ctypes.byref(n)),
+                                               int(mode), rows.ctypes.data, offs.ctypes.data, MAX_LEVELS, ctypes.byref(n),
+                                               ctypes.byref(first_b)),
               "ps_lmconv_levels_host")
         offs = offs[:n.value + 1].copy() if n.value else np.zeros(1, np.int32)
-        return rows[:int(offs[-1])], offs
+        return rows[:int(offs[-1])], offs, first_b.value
 
     def _run(self, codes, order, words, sample_mask, uniforms, temperature, mode):
         dev = self.device
         B = codes.shape[0]
         wn = words.detach().cpu().numpy() if torch.is_tensor(words) else np.asarray(words)
         ordn = order.detach().cpu().numpy() if torch.is_tensor(order) else np.asarray(order)
-        rows, offs = self.levels_host(ordn, wn, sample_mask, mode)
-        self.last_levels = offs
+        rows, offs, first_b = self.levels_host(ordn, wn, sample_mask, mode)
+        self.last_levels, self.last_first_b = offs, first_b
         codes_d = torch.as_tensor(codes).to(device=dev, dtype=torch.int64).reshape(B, 1024).clone()
         logits = torch.empty((B, 1024, 512), dtype=torch.float32, device=dev) if mode == 1 else None
         if len(offs) > 1:
@@ -235,7 +234,7 @@ class LmconvB200:
                 self._cache = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(self.wblob.device):
                 check(_lib.lib().ps_lmconv_tc_run(
-                    ctypes.byref(self.plan), B, rows_d.data_ptr(), offs.ctypes.data, len(offs) - 1, codes_d.data_ptr(),
+                    ctypes.byref(self.plan), B, rows_d.data_ptr(), offs.ctypes.data, len(offs) - 1, first_b, codes_d.data_ptr(),
                     None if uni_d is None else uni_d.data_ptr(), 0 if uni_d is None else uni_d.shape[1], float(temperature),
                     None if logits is None else logits.data_ptr(), self._cache.data_ptr(), nbytes,
                     torch.cuda.current_stream().cuda_stream), "ps_lmconv_tc_run")

@@ -30,9 +30,10 @@ def _decode(rows):
 
 def test_levels_are_wavefronts_of_independent_cells():
     lm, order, words, smask = _cases()
-    rows, offs = lm.LmconvB200.levels_host(order, words, smask, 0)
+    rows, offs, first_b = lm.LmconvB200.levels_host(order, words, smask, 0)
     b, cell, w0, w1, w2, flags, uidx = _decode(rows)
     B = len(order)
+    assert 0 < first_b < len(offs) - 1
     level = np.full((B, 1024), -1)
     for l in range(len(offs) - 1):
         level[b[offs[l]:offs[l + 1]], cell[offs[l]:offs[l + 1]]] = l
@@ -51,9 +52,17 @@ def test_levels_are_wavefronts_of_independent_cells():
                 for t in range(9):
                     if t != 4 and (words[i, m, c] >> t) & 1:
                         deps.append(c + ((t // 3 - 1) * 32 + (t % 3 - 1)) * dil)
-            # every masked-in neighbour sits on a strictly lower level, and one of them directly below
+            # every masked-in neighbour sits on a strictly lower level
             assert all(0 <= level[i, d] < level[i, c] for d in deps)
-            assert level[i, c] == (max(level[i, d] for d in deps) + 1 if deps else 0)
+            # phase B = sampled cells and whatever has one among its ancestors; the levels before first_b are the
+            # known prefix.  Within its phase a cell sits directly above the highest of its same-phase neighbours.
+            in_b = bool(smask[i, c]) or any(level[i, d] >= first_b for d in deps)
+            assert (level[i, c] >= first_b) == in_b
+            if in_b:
+                below = [level[i, d] for d in deps if level[i, d] >= first_b]
+                assert level[i, c] == (max(below) + 1 if below else first_b)
+            else:
+                assert level[i, c] == (max(level[i, d] for d in deps) + 1 if deps else 0)
     # rows carry the masks, the sampled flag and the index of their uniform number (rank among the sampled cells)
     assert np.array_equal(w0, words[b, 0, cell]) and np.array_equal(w1, words[b, 1, cell]) and np.array_equal(w2, words[b, 2, cell])
     assert np.array_equal((flags & 1).astype(bool), smask[b, cell]) and np.all(flags & 4)
@@ -62,22 +71,23 @@ def test_levels_are_wavefronts_of_independent_cells():
         got = {int(c): int(u) for bb, c, u, f in zip(b, cell, uidx, flags) if bb == i and f & 1}
         assert got == {int(c): k for k, c in enumerate(seq)}
     # the half-plane case of BASELINE configs[2]: 512 sampled cells in < 100 wavefronts instead of 512 serial steps
-    n_half = level[B - 1].max() + 1
+    n_half = level[B - 1].max() + 1 - first_b
     assert smask[B - 1].sum() == 512 and n_half < 100
 
 
 def test_logits_mode_levels_every_cell():
     lm, order, words, smask = _cases()
-    rows, offs = lm.LmconvB200.levels_host(order[:2], words[:2], None, 1)
+    rows, offs, first_b = lm.LmconvB200.levels_host(order[:2], words[:2], None, 1)
     b, cell, w0, w1, w2, flags, uidx = _decode(rows)
+    assert first_b == len(offs) - 1          # teacher forcing: every level is prefix
     assert len(rows) == 2048 and np.all(flags & 2) and not np.any(flags & 1)
     assert sorted(zip(b.tolist(), cell.tolist())) == [(i, c) for i in range(2) for c in range(1024)]
 
 
 def test_images_with_nothing_to_sample_produce_no_rows():
     lm, order, words, smask = _cases()
-    rows, offs = lm.LmconvB200.levels_host(order[:2], words[:2], np.zeros((2, 1024), np.uint8), 0)
-    assert len(rows) == 0 and len(offs) == 1
+    rows, offs, first_b = lm.LmconvB200.levels_host(order[:2], words[:2], np.zeros((2, 1024), np.uint8), 0)
+    assert len(rows) == 0 and len(offs) == 1 and first_b == 0
 
 
 def test_weight_schedule_tiles_reproduce_the_layers():
@@ -89,7 +99,7 @@ def test_weight_schedule_tiles_reproduce_the_layers():
     sd = weights.make_state("lmconv", 0)
     m = lm.LmconvB200(sd, device="cpu")
     dt = np.dtype([("w", np.uint32), ("rows", np.uint16), ("kind", np.uint8), ("t", np.uint8), ("mask", np.uint8),
-                   ("cin8", np.uint8), ("kc", np.uint8), ("off", np.uint8), ("col", np.uint16), ("fl", np.uint8), ("pad", np.uint8)])
+                   ("cin8", np.uint8), ("kc", np.uint8), ("off", np.uint8), ("col", np.uint16), ("fl", np.uint8), ("gemm", np.uint8)])
     ch = np.frombuffer(m.chunks.numpy().tobytes(), dtype=dt)
     blob = m.wblob.numpy()
 
@@ -108,11 +118,14 @@ def test_weight_schedule_tiles_reproduce_the_layers():
     assert np.array_equal(got, nc) and all(ch[i]["kind"] == 0 and ch[i]["kc"] == i for i in range(20))
     ctr = np.concatenate([tile(ch[i]) for i in range(20, 23)], 1)
     assert np.array_equal(ctr[:, :160], w9[:, 4].half().float().numpy()) and not ctr[:, 160:].any()
-    assert all(ch[i]["kind"] == 2 for i in range(20, 23)) and ch[22]["fl"] & 2 and m.plan.epi_first[0] == 20
+    assert all(ch[i]["kind"] == 3 for i in range(20, 23)) and ch[22]["fl"] & 2 and m.plan.epi_first[0] == 20
+    assert all(ch[i]["gemm"] == 0 for i in range(23)) and ch[23]["gemm"] == 1
     # accumulate flags: only the first chunk of an accumulator overwrites
     assert not ch[0]["fl"] & 1 and all(ch[i]["fl"] & 1 for i in range(1, 23))
-    # exactly one stage-release point per GEMM that needs one, STAGES before its last centre chunk
+    # the issuer waits for the epilogue's operand at the first centre chunk of each of the 32 body GEMMs
     rel = [i for i in range(len(ch)) if ch[i]["fl"] & 16]
-    assert len(rel) == 33 and rel[0] == 22 - lm.STAGES
+    assert rel == [m.plan.epi_first[g] for g in range(32)]
+    # nin_out: quarter 0's operand is written into its ring stages, quarters 1-3 re-read it
+    assert [int(c["kind"]) for c in ch[-8:]] == [2, 2, 4, 4, 4, 4, 4, 4] and m.plan.raw_mask == sum(1 << t for t in (4, 8, 18, 24))
     # the last quarter of nin_out ends the schedule and completes the logits barrier
     assert ch[-1]["fl"] & 2 and (ch[-1]["fl"] >> 2) & 3 == 2 and ch[-1]["col"] == 384

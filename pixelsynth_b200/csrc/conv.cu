@@ -12,10 +12,12 @@
 // 128-byte-swizzled K-major layout tcgen05 consumes directly.  A second input tensor with its own taps can be
 // accumulated into the same tile (the decoder's 1x1 skip convolution, blocks.py:43,65-66).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (each reads its 32-lane TMEM quadrant with tcgen05.ld, applies bias / residual /
-// per-sample scale+shift / activation and writes up to two NHWC outputs).  smem ring of STAGES stages guarded by
-// full/empty mbarriers; MMA completion is signalled with tcgen05.commit.
+// Persistent kernel, one CTA per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Warp roles (192
+// threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (each reads its
+// 32-lane TMEM quadrant with tcgen05.ld, applies bias / residual / per-sample scale+shift / activation and writes up
+// to two NHWC outputs).  The smem ring of `stages` stages (full/empty mbarriers) runs on across tiles, and the
+// accumulator is double buffered in TMEM (acc_full / acc_empty mbarriers), so the epilogue of tile i overlaps the
+// main loop of tile i + 1.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -28,11 +30,13 @@ constexpr int CONV_THREADS = 192;
 constexpr int BM = 128;  // output pixels per tile (UMMA M)
 constexpr int BK = 64;   // channels per K step (128 bytes of bf16 = one swizzle row)
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int CONV_MAX_STAGES = 8;
 
 struct ConvKernelParams {
   // tile geometry: TW * TH * TN == 128
   int TW, TH, TN;
   int tiles_x, tiles_y;
+  int tiles_spatial, total_tiles;  // tile index = column block * tiles_spatial + spatial tile
   int Hout, Wout, N;  // output grid this launch computes (per phase for transposed convs)
   int stride;         // input pixel = out * stride + tap offset
   int ntaps[2], kchunks[2];
@@ -71,29 +75,53 @@ __device__ __forceinline__ float apply_act(float v, int act, const float* ap) {
   }
 }
 
+// y[0..32) = act(f * scale + shift) -> 64 bytes of bf16 at dst (16-byte aligned); the activation is a compile-time
+// constant here so the 32-wide loop carries no switch
+template <int ACT>
+__device__ __forceinline__ void store_block32(const float* f, const float* sc, const float* sh, const float* ap,
+                                              __nv_bfloat16* dst) {
+  float y[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sc) a = __ldg(reinterpret_cast<const float4*>(sc + j));
+    if (sh) b = __ldg(reinterpret_cast<const float4*>(sh + j));
+    y[j] = apply_act(fmaf(f[j], a.x, b.x), ACT, ap);
+    y[j + 1] = apply_act(fmaf(f[j + 1], a.y, b.y), ACT, ap);
+    y[j + 2] = apply_act(fmaf(f[j + 2], a.z, b.z), ACT, ap);
+    y[j + 3] = apply_act(fmaf(f[j + 3], a.w, b.w), ACT, ap);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(y[j], y[j + 1]), h1 = __floats2bfloat162_rn(y[j + 2], y[j + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(y[j + 4], y[j + 5]), h3 = __floats2bfloat162_rn(y[j + 6], y[j + 7]);
+    uint4 w;
+    w.x = *reinterpret_cast<uint32_t*>(&h0);
+    w.y = *reinterpret_cast<uint32_t*>(&h1);
+    w.z = *reinterpret_cast<uint32_t*>(&h2);
+    w.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(dst + j) = w;
+  }
+}
+
 __global__ void __launch_bounds__(CONV_THREADS, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapW, const ConvKernelParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform to the compiler as well
   const int BN = p.BN;
+  const int BNp = (BN + 31) & ~31;  // TMEM columns per accumulator buffer
   const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
   // carve: [stages x (A | B)] then barriers
   unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(tiles + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* accum_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
-
-  // tile coordinates
-  int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x;
-  tile /= p.tiles_x;
-  const int ty = tile % p.tiles_y;
-  const int tn = tile / p.tiles_y;
-  const int ox0 = tx * p.TW, oy0 = ty * p.TH, n0 = tn * p.TN;
-  const int ncol0 = blockIdx.y * BN;
+  uint64_t* acc_full = empty_bar + p.stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
   const int kiters = p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1];
+  const uint32_t ncols = 2 * BNp <= 32 ? 32u : (2 * BNp <= 64 ? 64u : (2 * BNp <= 128 ? 128u : (2 * BNp <= 256 ? 256u : 512u)));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -106,60 +134,68 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
-      mbar_init(accum_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&acc_full[b], 1);
+        mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+      }
+      mbar_fence_init();
     }
     __syncwarp();
-    // TMEM: power-of-two column count >= 32 covering BN fp32 columns
-    const uint32_t ncols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(tmem_slot, ncols);
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int src = 0; src < 2; ++src) {
-        const CUtensorMap* mA = src ? &mapA1 : &mapA0;
-        for (int t = 0; t < p.ntaps[src]; ++t) {
-          const int ix0 = ox0 * p.stride + p.dx[src][t];
-          const int iy0 = oy0 * p.stride + p.dy[src][t];
-          for (int kc = 0; kc < p.kchunks[src]; ++kc, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            unsigned char* a = tiles + (size_t)s * stage_bytes;
-            mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-            tma_load_4d(mA, &full_bar[s], a, kc * BK, ix0, iy0, n0);
-            tma_load_2d(&mapW, &full_bar[s], a + A_STAGE_BYTES, kc * BK, p.wrow[src][t] + ncol0);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
+        const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx * p.TW, oy0 = ty * p.TH, n0 = tn * p.TN, ncol0 = cb * BN;
+        for (int src = 0; src < 2; ++src) {
+          const CUtensorMap* mA = src ? &mapA1 : &mapA0;
+          for (int t = 0; t < p.ntaps[src]; ++t) {
+            const int ix0 = ox0 * p.stride + p.dx[src][t];
+            const int iy0 = oy0 * p.stride + p.dy[src][t];
+            for (int kc = 0; kc < p.kchunks[src]; ++kc, ++it) {
+              const int s = it % p.stages;
+              const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              unsigned char* a = tiles + (size_t)s * stage_bytes;
+              mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+              tma_load_4d(mA, &full_bar[s], a, kc * BK, ix0, iy0, n0);
+              tma_load_2d(&mapW, &full_bar[s], a + A_STAGE_BYTES, kc * BK, p.wrow[src][t] + ncol0);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: whole warp, warp-uniform operands, one elected lane issues (tc05.cuh: umma_f16_kblock) =====
     const uint32_t idesc = umma_idesc_bf16(BN);
-    for (int it = 0; it < kiters; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-      mbar_wait(&full_bar[s], ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t a = smem_u32(tiles + (size_t)s * stage_bytes);
-        const uint32_t b = a + A_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(tmem_base, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, (it | k) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);                      // frees the smem stage once these MMAs have read it
-        if (it == kiters - 1) umma_commit(accum_bar);    // accumulator complete
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
+    int s = 0, lt = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(&acc_empty[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(buf * BNp);
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4);
+        umma_f16_kblock(d, a_lo, a_lo + (A_STAGE_BYTES >> 4), idesc, it ? 1u : 0u, &empty_bar[s]);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      __syncwarp();
+      umma_commit_elect(&acc_full[buf]);  // accumulator complete
     }
   } else {
     // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
@@ -167,93 +203,118 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     const int m = q * 32 + lane;  // tile row = output pixel
     const int nl = m / (p.TH * p.TW);
     const int rem = m - nl * (p.TH * p.TW);
-    const int oy = oy0 + rem / p.TW, ox = ox0 + rem % p.TW;
-    const int n = n0 + nl;
-    const bool valid = n < p.N && oy < p.Hout && ox < p.Wout;
-    const int fy = oy * p.out_sy + p.out_py, fx = ox * p.out_sx + p.out_px;
-    const size_t pixel = ((size_t)n * p.out_H + fy) * p.out_W + fx;
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (!valid) continue;
-      const int cbase = ncol0 + c0;
-      if (cbase >= p.Cout) continue;
-      float f[32];
+    const int my = rem / p.TW, mx = rem % p.TW;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
+      const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
+      const int oy = ty * p.TH + my, ox = tx * p.TW + mx, n = tn * p.TN + nl, ncol0 = cb * BN;
+      const bool valid = n < p.N && oy < p.Hout && ox < p.Wout;
+      const int fy = oy * p.out_sy + p.out_py, fx = ox * p.out_sx + p.out_px;
+      const size_t pixel = ((size_t)n * p.out_H + fy) * p.out_W + fx;
+      const int buf = lt & 1;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BNp);
+      mbar_wait(&acc_full[buf], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tbase + (uint32_t)c0, v);
+        const int cbase = ncol0 + c0;
+        if (!valid || cbase >= p.Cout) continue;
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        f[j] = __uint_as_float(v[j]);
-        const int c = cbase + j;
-        if (p.bias && c < p.Cout) f[j] += __ldg(p.bias + c);
-      }
-      if (p.residual) {
-        const __nv_bfloat16* r = p.residual + pixel * p.res_cstride + cbase;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cbase + j < p.Cout) f[j] += __bfloat162float(r[j]);
-      }
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        if (!p.out[o]) continue;
-        const float* sc = p.scale[o] ? p.scale[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) : nullptr;
-        const float* sh = p.shift[o] ? p.shift[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) : nullptr;
-        __nv_bfloat16* dst = p.out[o] + pixel * p.out_cstride[o] + p.out_coffset[o] + cbase;
-        float y[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = cbase + j;
-          float t = f[j];
-          if (c < p.Cout) {
-            if (sc) t *= __ldg(sc + c);
-            if (sh) t += __ldg(sh + c);
-          }
-          y[j] = apply_act(t, p.act[o], p.act_param);
-        }
-        const bool full = cbase + 32 <= p.Cout && ((((uintptr_t)dst) & 15) == 0);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const bool full = cbase + 32 <= p.Cout && (p.Cout & 3) == 0;
         if (full) {
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(y[j], y[j + 1]), h1 = __floats2bfloat162_rn(y[j + 2], y[j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(y[j + 4], y[j + 5]), h3 = __floats2bfloat162_rn(y[j + 6], y[j + 7]);
-            uint4 w;
-            w.x = *reinterpret_cast<uint32_t*>(&h0);
-            w.y = *reinterpret_cast<uint32_t*>(&h1);
-            w.z = *reinterpret_cast<uint32_t*>(&h2);
-            w.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(dst + j) = w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+              f[j] += b4.x;
+              f[j + 1] += b4.y;
+              f[j + 2] += b4.z;
+              f[j + 3] += b4.w;
+            }
+          }
+          if (p.residual) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.residual + pixel * p.res_cstride + cbase);
+            uint4 rv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = __ldg(r + j);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[j]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 t2 = __bfloat1622float2(h[k]);
+                f[8 * j + 2 * k] += t2.x;
+                f[8 * j + 2 * k + 1] += t2.y;
+              }
+            }
           }
         } else {
-          for (int j = 0; j < 32; ++j)
-            if (cbase + j < p.Cout) dst[j] = __float2bfloat16(y[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            if (p.bias && c < p.Cout) f[j] += __ldg(p.bias + c);
+          }
+          if (p.residual) {
+            const __nv_bfloat16* r = p.residual + pixel * p.res_cstride + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.Cout) f[j] += __bfloat162float(r[j]);
+          }
         }
-        if (o == 0 && p.out_f32_nchw) {
-          for (int j = 0; j < 32; ++j)
-            if (cbase + j < p.Cout)
-              p.out_f32_nchw[(((size_t)n * p.Cout + cbase + j) * p.out_H + fy) * p.out_W + fx] = y[j];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (!p.out[o]) continue;
+          const float* sc = p.scale[o] ? p.scale[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
+          const float* sh = p.shift[o] ? p.shift[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
+          __nv_bfloat16* dst = p.out[o] + pixel * p.out_cstride[o] + p.out_coffset[o] + cbase;
+          if (full && ((((uintptr_t)dst) & 15) == 0)) {
+            switch (p.act[o]) {
+              case ACT_RELU: store_block32<ACT_RELU>(f, sc, sh, p.act_param, dst); break;
+              case ACT_LEAKY: store_block32<ACT_LEAKY>(f, sc, sh, p.act_param, dst); break;
+              case ACT_NONE: store_block32<ACT_NONE>(f, sc, sh, p.act_param, dst); break;
+              default:
+                for (int j = 0; j < 32; ++j) {
+                  float t = f[j];
+                  if (sc) t *= __ldg(sc + j);
+                  if (sh) t += __ldg(sh + j);
+                  dst[j] = __float2bfloat16(apply_act(t, p.act[o], p.act_param));
+                }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              if (cbase + j >= p.Cout) break;
+              float t = f[j];
+              if (sc) t *= __ldg(sc + j);
+              if (sh) t += __ldg(sh + j);
+              dst[j] = __float2bfloat16(apply_act(t, p.act[o], p.act_param));
+            }
+          }
         }
-      }
-      if (!p.out[0] && p.out_f32_nchw) {  // fp32-only output
-        const float* sc = p.scale[0] ? p.scale[0] + (p.per_sample[0] ? (size_t)n * p.Cout : 0) : nullptr;
-        const float* sh = p.shift[0] ? p.shift[0] + (p.per_sample[0] ? (size_t)n * p.Cout : 0) : nullptr;
-        for (int j = 0; j < 32; ++j) {
-          const int c = cbase + j;
-          if (c < p.Cout) {
+        if (p.out_f32_nchw) {  // fp32 NCHW copy of output 0's values (or the only output)
+          const float* sc = p.scale[0] ? p.scale[0] + (p.per_sample[0] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
+          const float* sh = p.shift[0] ? p.shift[0] + (p.per_sample[0] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            if (c >= p.Cout) break;
             float t = f[j];
-            if (sc) t *= __ldg(sc + c);
-            if (sh) t += __ldg(sh + c);
+            if (sc) t *= __ldg(sc + j);
+            if (sh) t += __ldg(sh + j);
             p.out_f32_nchw[(((size_t)n * p.Cout + c) * p.out_H + fy) * p.out_W + fx] = apply_act(t, p.act[0], p.act_param);
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    const uint32_t ncols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
-  }
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -350,8 +411,9 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   PS_CHECK_ARG(d->cout_pad % BN == 0);
   p.BN = BN;
   const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
-  // <= 128 columns: 3 stages (97 KB) so two CTAs share an SM and one's epilogue overlaps the other's main loop
-  const int stages = BN <= 128 ? 3 : 4;
+  // one persistent CTA per SM: as many ring stages as ~200 KB of shared memory hold
+  int stages = (200 * 1024) / stage_bytes;
+  stages = stages > CONV_MAX_STAGES ? CONV_MAX_STAGES : (stages < 2 ? 2 : stages);
   p.stages = stages;
   CUtensorMap mapA[2], mapW;
   memset(mapA, 0, sizeof(mapA));
@@ -399,15 +461,19 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.out_py = d->out_py;
   p.out_px = d->out_px;
 
-  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
   static thread_local int attr_dev = -1;
+  static thread_local int sms = 148;
   int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
   if (attr_dev != dev) {
     PS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr_dev = dev;
   }
-  dim3 grid(p.tiles_x * p.tiles_y * tiles_n, d->cout_pad / BN);
+  p.tiles_spatial = p.tiles_x * p.tiles_y * tiles_n;
+  p.total_tiles = p.tiles_spatial * (d->cout_pad / BN);
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   PS_TIME_BEGIN("conv_igemm_kernel", (cudaStream_t)stream);
   conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, (cudaStream_t)stream>>>(mapA[0], mapA[1], mapW, p);
   PS_TIME_END((cudaStream_t)stream);

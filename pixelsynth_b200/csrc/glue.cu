@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <queue>
 #include <tuple>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -126,33 +127,46 @@ using namespace ps;
 extern "C" int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, int* dist_host, int* order_host,
                                    uint16_t* words_host, uint8_t* sample_mask_host) {
   PS_CHECK_ARG(bg_mask_host && order_host && words_host && sample_mask_host && B >= 0 && S == 8 * G);
-  std::vector<uint8_t> fg(G * G), bg(G * G);
-  std::vector<float> fd(G * G), bd(G * G);
-  std::vector<long long> d(G * G);
-  for (int b = 0; b < B; ++b) {
-    const uint8_t* m = bg_mask_host + (size_t)b * S * S;
-    for (int r = 0; r < G; ++r)
-      for (int c = 0; c < G; ++c) {
-        int cnt = 0;
-        for (int y = 0; y < 8; ++y)
-          for (int x = 0; x < 8; ++x) cnt += m[(size_t)(r * 8 + y) * S + c * 8 + x] ? 1 : 0;
-        bg[r * G + c] = cnt == 64;  // AvgPool2d(8) -> astype(uint8): 1 only when every pixel agrees
-        fg[r * G + c] = cnt == 0;
-        sample_mask_host[(size_t)b * G * G + r * G + c] = cnt == 64;  // sample.py:29 `== 1`
+  // images are independent: a few host threads share them (the GPU is waiting for this result)
+  auto work = [&](int b0, int b1) {
+    std::vector<uint8_t> fg(G * G), bg(G * G);
+    std::vector<float> fd(G * G), bd(G * G);
+    std::vector<long long> d(G * G);
+    for (int b = b0; b < b1; ++b) {
+      const uint8_t* m = bg_mask_host + (size_t)b * S * S;
+      for (int r = 0; r < G; ++r)
+        for (int c = 0; c < G; ++c) {
+          int cnt = 0;
+          for (int y = 0; y < 8; ++y)
+            for (int x = 0; x < 8; ++x) cnt += m[(size_t)(r * 8 + y) * S + c * 8 + x] ? 1 : 0;
+          bg[r * G + c] = cnt == 64;  // AvgPool2d(8) -> astype(uint8): 1 only when every pixel agrees
+          fg[r * G + c] = cnt == 0;
+          sample_mask_host[(size_t)b * G * G + r * G + c] = cnt == 64;  // sample.py:29 `== 1`
+        }
+      chamfer5x5(fg.data(), G, G, fd.data());
+      chamfer5x5(bg.data(), G, G, bd.data());
+      for (int i = 0; i < G * G; ++i) {
+        // a transform with no zero cell saturates as OpenCV 4.2 did ((UINT_MAX - LONG_DIST) / 65536): the FLT_MAX of
+        // newer builds does not survive the reference's astype(int)
+        const float sat = (float)((4294967295.0 - 143976.0) / 65536.0);
+        const double v = (double)std::min(fd[i], sat) - (double)std::min(bd[i], sat);  // float64, z_buffermodel.py:670-675
+        d[i] = (long long)v;                             // astype(int) truncates toward zero
+        if (dist_host) dist_host[(size_t)b * G * G + i] = (int)d[i];
+        d[i] *= 10000;                                   // get_custom_order.pyx:26
       }
-    chamfer5x5(fg.data(), G, G, fd.data());
-    chamfer5x5(bg.data(), G, G, bd.data());
-    for (int i = 0; i < G * G; ++i) {
-      // a transform with no zero cell saturates as OpenCV 4.2 did ((UINT_MAX - LONG_DIST) / 65536): the FLT_MAX of
-      // newer builds does not survive the reference's astype(int)
-      const float sat = (float)((4294967295.0 - 143976.0) / 65536.0);
-      const double v = (double)std::min(fd[i], sat) - (double)std::min(bd[i], sat);  // float64, z_buffermodel.py:670-675
-      d[i] = (long long)v;                             // astype(int) truncates toward zero
-      if (dist_host) dist_host[(size_t)b * G * G + i] = (int)d[i];
-      d[i] *= 10000;                                   // get_custom_order.pyx:26
+      custom_order(d.data(), order_host + (size_t)b * G * G);
+      mask_words(order_host + (size_t)b * G * G, words_host + (size_t)b * 3 * G * G);
     }
-    custom_order(d.data(), order_host + (size_t)b * G * G);
-    mask_words(order_host + (size_t)b * G * G, words_host + (size_t)b * 3 * G * G);
+  };
+  unsigned hw = std::thread::hardware_concurrency();
+  int nth = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+  nth = std::min(nth, B / 2);  // at least two images per thread
+  if (nth <= 1) {
+    work(0, B);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; ++t) th.emplace_back(work, (int)((long long)B * t / nth), (int)((long long)B * (t + 1) / nth));
+    for (auto& x : th) x.join();
   }
   return PS_OK;
 }

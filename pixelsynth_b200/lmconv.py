@@ -68,7 +68,10 @@ def glue_host(background_mask):
     """ZbufferModelPts.get_masks_for_batch (z_buffermodel.py:641-701) in native host code.
     background_mask (B,256,256) bool tensor (any device) -> numpy dist (B,32,32) i32, order (B,1024) i32,
     words (B,3,1024) u16, sample_mask (B,32,32) bool."""
-    m = np.ascontiguousarray(background_mask.detach().to("cpu").numpy().astype(np.uint8))
+    if isinstance(background_mask, np.ndarray):
+        m = np.ascontiguousarray(background_mask.astype(np.uint8, copy=False))
+    else:
+        m = np.ascontiguousarray(background_mask.detach().to("cpu").numpy().astype(np.uint8))
     B, S, _ = m.shape
     dist = np.zeros((B, 32, 32), np.int32)
     order = np.zeros((B, 1024), np.int32)
@@ -197,6 +200,7 @@ class LmconvB200:
         self.plan.wblob, self.plan.chunks = self.wblob.data_ptr(), self.chunks.data_ptr()
         self.plan.w_uinit, self.plan.bias = self.w_uinit.data_ptr(), self.bias.data_ptr()
         self._cache = None
+        self._rows_pin = self._rows_dev = self._rows_evt = None
         self.last_levels = None
 
     @staticmethod
@@ -217,18 +221,41 @@ class LmconvB200:
         offs = offs[:n.value + 1].copy() if n.value else np.zeros(1, np.int32)
         return rows[:int(offs[-1])], offs, first_b.value
 
-    def _run(self, codes, order, words, sample_mask, uniforms, temperature, mode):
-        dev = self.device
-        B = codes.shape[0]
+    def prepare(self, order, words, sample_mask, mode=0):
+        """Host half of a sampler call: dependency levels of (order, words, sample_mask) and the upload of the row
+        records (pinned staging, asynchronous).  The result can be passed to sample()/logits() as `prepared`, so the
+        host work overlaps whatever the GPU is doing in between."""
         wn = words.detach().cpu().numpy() if torch.is_tensor(words) else np.asarray(words)
         ordn = order.detach().cpu().numpy() if torch.is_tensor(order) else np.asarray(order)
-        rows, offs, first_b = self.levels_host(ordn, wn, sample_mask, mode)
+        smn = None
+        if sample_mask is not None:
+            smn = sample_mask.detach().cpu().numpy() if torch.is_tensor(sample_mask) else np.asarray(sample_mask)
+            smn = smn.astype(np.uint8)
+        rows, offs, first_b = self.levels_host(ordn, wn, smn, mode)
+        rows_d = None
+        if len(offs) > 1:
+            n = rows.shape[0]
+            if self._rows_pin is None or self._rows_pin.shape[0] < n:
+                self._rows_pin = torch.empty((max(n, 1024), 16), dtype=torch.uint8).pin_memory()
+                self._rows_dev = torch.empty((self._rows_pin.shape[0], 16), dtype=torch.uint8, device=self.device)
+            if self._rows_evt is not None:
+                self._rows_evt.synchronize()      # the previous upload has left the staging buffer
+            self._rows_pin[:n].numpy()[:] = rows
+            rows_d = self._rows_dev[:n]
+            rows_d.copy_(self._rows_pin[:n], non_blocking=True)
+            self._rows_evt = torch.cuda.Event()
+            self._rows_evt.record()
+        return dict(rows=rows_d, offs=offs, first_b=first_b, mode=mode)
+
+    def _run(self, codes, prepared, uniforms, temperature):
+        dev = self.device
+        B = codes.shape[0]
+        offs, first_b, mode, rows_d = prepared["offs"], prepared["first_b"], prepared["mode"], prepared["rows"]
         self.last_levels, self.last_first_b = offs, first_b
         codes_d = torch.as_tensor(codes).to(device=dev, dtype=torch.int64).reshape(B, 1024).clone()
         logits = torch.empty((B, 1024, 512), dtype=torch.float32, device=dev) if mode == 1 else None
         if len(offs) > 1:
-            rows_d = torch.from_numpy(rows).to(dev)
-            uni_d = None if uniforms is None else torch.as_tensor(uniforms).to(device=dev, dtype=torch.float32).reshape(B, -1).contiguous()
+            uni_d = None if uniforms is None else torch.as_tensor(uniforms).to(device=dev, dtype=torch.float32, non_blocking=True).reshape(B, -1).contiguous()
             nbytes = _lib.lib().ps_lmconv_tc_cache_bytes(B)
             if self._cache is None or self._cache.numel() < nbytes:
                 self._cache = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -240,15 +267,16 @@ class LmconvB200:
                     torch.cuda.current_stream().cuda_stream), "ps_lmconv_tc_run")
         return codes_d.view(B, 32, 32), logits
 
-    def sample(self, codes, order, words, sample_mask, uniforms, temperature=1.0):
+    def sample(self, codes, order, words, sample_mask, uniforms, temperature=1.0, prepared=None):
         """codes (B,32,32) int64 with the known cells; returns codes with the sample_mask cells drawn in generation
         order (the argmax of sample.py's one-hot `data`, as z_buffermodel.py:249 takes it)."""
-        smn = sample_mask.detach().cpu().numpy() if torch.is_tensor(sample_mask) else np.asarray(sample_mask)
-        out, _ = self._run(codes, order, words, smn.astype(np.uint8), uniforms, temperature, 0)
+        if prepared is None:
+            prepared = self.prepare(order, words, sample_mask, 0)
+        out, _ = self._run(codes, prepared, uniforms, temperature)
         return out
 
     def logits(self, codes, order, words):
         """Teacher-forced logits of every cell given all codes: (B,512,32,32) like OurPixelCNN.forward."""
         B = codes.shape[0]
-        _, lg = self._run(codes, order, words, None, None, 1.0, 1)
+        _, lg = self._run(codes, self.prepare(order, words, None, 1), None, 1.0)
         return lg.view(B, 32, 32, 512).permute(0, 3, 1, 2).contiguous()

@@ -81,6 +81,8 @@ class ZbufferModelPts(nn.Module):
                                                 bool(_get(opt, "normalize_before_residual", False)))
         self.obs = [3, 32, 32]
         self.ranker = None
+        self._bg_pin = None
+        self._prepared = None
 
     # -- z_buffermodel.py:120-184 ---------------------------------------------------------------
     def process_batch(self, batch):
@@ -152,7 +154,8 @@ class ZbufferModelPts(nn.Module):
         B = codes.shape[0]
         for i in range(n):
             u = uniforms if uniforms is not None else self._sampler_uniforms(i, B)
-            sampled = self.outpaint2.sample(codes, order, words, sample_mask, u, float(_get(self.opt, "temperature", 1.0)))
+            sampled = self.outpaint2.sample(codes, order, words, sample_mask, u, float(_get(self.opt, "temperature", 1.0)),
+                                            prepared=getattr(self, "_prepared", None))
             ar_sample = self.vqvae.decode_code(sampled)
             combined = self.get_combined(gen_fs, ar_sample, background_mask)
             imgs.append(self.projector.forward(combined, background_mask, noise))
@@ -189,8 +192,18 @@ class ZbufferModelPts(nn.Module):
         if _get(self.opt, "no_outpainting", False):
             raise NotImplementedError("no_outpainting (3-channel decoder, SynSin baseline) is not the shipped configuration")
         else:
-            _, order, words, sample_mask = self.get_masks_for_batch(output_RT, input_RTinv, background_mask)
+            # The generation order / masks / dependency levels are host work on the background mask (native code,
+            # csrc/glue.cu + ps_lmconv_levels_host).  The mask goes to pinned memory behind an event, the VQ-VAE
+            # encoder is queued, and the host part runs while the GPU encodes.
+            if self._bg_pin is None or self._bg_pin.shape != background_mask.shape:
+                self._bg_pin = torch.empty(background_mask.shape, dtype=torch.uint8).pin_memory()
+            self._bg_pin.copy_(background_mask.view(torch.uint8), non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record()
             codes = self.vqvae.encode_top(gen_fs)
+            ready.synchronize()
+            _, order, words, sample_mask = self.get_masks_for_batch(output_RT, input_RTinv, self._bg_pin.numpy())
+            self._prepared = self.outpaint2.prepare(order, words, sample_mask, 0)
             gen_img = self.get_best_sample(order, words, sample_mask, codes, background_mask, gen_fs, netD, input_img,
                                            noise, uniforms)
             self.last = dict(depth=regressed_pts, gen_fs=gen_fs, background_mask=background_mask, order=order, words=words,

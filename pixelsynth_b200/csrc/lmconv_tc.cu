@@ -254,8 +254,8 @@ __device__ __noinline__ unsigned int wait_progress(const unsigned int* prog, int
 }
 
 // 16-byte group kg (0..7) of row r of the A tile in the ring stage of schedule chunk `chunk` (128-byte swizzle)
-__device__ __forceinline__ void sts_a(unsigned char* tiles, int stage, int stage_bytes, int kg, int r, uint4 v) {
-  const uint32_t addr = smem_u32(tiles + (size_t)stage * stage_bytes) + r * 128 + ((kg ^ (r & 7)) << 4);
+__device__ __forceinline__ void sts_a(unsigned char* tiles, int slot_offset, int kg, int r, uint4 v) {
+  const uint32_t addr = smem_u32(tiles + slot_offset) + r * 128 + ((kg ^ (r & 7)) << 4);
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
@@ -341,10 +341,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   const unsigned int* prog = p.sync + 16;
   // Ring geometry: the A tile of a stage holds only the tile's rows (rounded up to 8); the MMA still reads 128 rows
   // and runs on into the stage's weight tile, which only feeds accumulator lanes nobody looks at.
+  // A ring stage holds TWO consecutive chunks (slot = chunk & 1), so the issuer pays one barrier wait, one proxy
+  // fence and one commit per eight MMAs.
   const int a_rows = (tile.nrows + 7) & ~7;
   const int a_bytes = a_rows * 128;
-  const int stage_bytes = a_bytes + TC_W_BYTES;
+  const int slot_bytes = a_bytes + TC_W_BYTES;
+  const int stage_bytes = 2 * slot_bytes;
   const int nst = min(TC_MAX_STAGES, (TC_STAGES * TC_STAGE_BYTES) / stage_bytes);
+  // byte offset of chunk i's slot in the ring
+  auto slot_off = [&](int i) { return ((i >> 1) % nst) * stage_bytes + (i & 1) * slot_bytes; };
 
   if (tid < 128) {
     ps_lmconv_row ri;
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < nst; ++s) {
-        mbar_init(&sm.full[s], 33);  // 32 arrivals of the row writers (a gather warp, or the weight producer's lanes for an operand that is not in the ring) + the weight copy
+        mbar_init(&sm.full[s], 66);  // per chunk: 32 arrivals of the row writers (a gather warp, or the weight producer's lanes for an operand that is not in the ring) + the weight copy
         mbar_init(&sm.empty[s], 1);
       }
       for (int i = 0; i < 3; ++i) mbar_init(&sm.acc_full[i], 1);
@@ -378,61 +383,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
 
   if (warp == 0) {
     // ===== weight producer: whole warp, warp-uniform values, one elected lane issues (see umma_f16_kblock) =====
-    int s = 0;
+    int st = 0;
     uint32_t ph = 1;
     for (int i = 0; i < nchunks; ++i) {
       uint2 raw = sm.sched[i];
       raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
-      mbar_wait(&sm.empty[s], ph);
+      if (!(i & 1)) mbar_wait(&sm.empty[st], ph);  // the stage's second chunk rides on the same phase
       if (lane == 0) TC_TRACE(3, i);
       const uint32_t bytes = ((raw.x >> 24) & 31u) << 10;  // w_rows * 128
       const uint32_t kind = raw.x >> 29;
-      if (kind == A_TMEM || kind == A_REUSE) mbar_arrive(&sm.full[s]);  // nobody writes rows into this stage
+      if (kind == A_TMEM || kind == A_REUSE) mbar_arrive(&sm.full[st]);  // nobody writes rows into this slot
       if (p.debug & 1) {
-        if (lane == 0) mbar_arrive(&sm.full[s]);
+        if (lane == 0) mbar_arrive(&sm.full[st]);
       } else {
-        bulk_load_elect(tiles + (size_t)s * stage_bytes + a_bytes, p.wblob + (size_t)(raw.x & 0xffffffu) * 16, bytes,
-                        &sm.full[s]);
+        bulk_load_elect(tiles + (size_t)st * stage_bytes + (i & 1) * slot_bytes + a_bytes,
+                        p.wblob + (size_t)(raw.x & 0xffffffu) * 16, bytes, &sm.full[st]);
       }
-      if (++s == nst) {
-        s = 0;
-        ph ^= 1u;
+      if (i & 1) {
+        if (++st == nst) {
+          st = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop with warp-uniform values; one elected lane issues =====
-    const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
+    const uint32_t ring_lo = umma_desc_lo(smem_u32(tiles));
     const uint32_t idesc0 = umma_idesc_f16(0);
-    int s = 0;
+    const uint32_t reuse_lo0 = ring_lo + (uint32_t)(slot_off(p.logit_first) >> 4);
+    const uint32_t reuse_lo1 = ring_lo + (uint32_t)(slot_off(p.logit_first + 1) >> 4);
+    int st = 0;
     uint32_t ph = 0, cph = 0;
-    for (int i = 0; i < nchunks; ++i) {
-      uint2 raw = sm.sched[i];
-      raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
-      raw.y = __shfl_sync(0xffffffffu, raw.y, 0);
-      const uint32_t flags = (raw.y >> 20) & 63u;
-      const uint32_t kind = raw.x >> 29;
-      mbar_wait(&sm.full[s], ph);
-      if (flags & 16u) {  // first centre chunk of a GEMM: the previous epilogue has finished the operand in TMEM
-        mbar_wait(&sm.cfull, cph);
-        cph ^= 1u;
-      }
-      fence_proxy_async();
+    uint2 nxt = sm.sched[0];
+    for (int i = 0; i < nchunks; i += 2) {
+      mbar_wait(&sm.full[st], ph);
+      if (!(p.debug & 64)) fence_proxy_async();
       tc_fence_after();
-      if (lane == 0) TC_TRACE(0, i);
-      const uint32_t idesc = idesc0 | (((raw.x >> 24) & 31u) << 17);       // N >> 3 = w_rows / 8
-      const uint32_t d = tmem_base + (((raw.y >> 15) & 31u) << 4);          // d_col
-      const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(a_bytes >> 4);
-      const uint32_t kc = (raw.y >> 9) & 31u;
-      if (kind == A_TMEM) {
-        umma_f16_ts_kblock(d, tmem_base + COL_A + kc * 32u, b_lo, idesc, flags & 1u, &sm.empty[s]);
-      } else {
-        // A_REUSE: the operand the epilogue wrote for nin_out's first quarter stays in that quarter's stages
-        const uint32_t sa = kind == A_REUSE ? (uint32_t)((p.logit_first + (int)kc) % nst) : (uint32_t)s;
-        umma_f16_kblock(d, a_lo0 + sa * (uint32_t)(stage_bytes >> 4), b_lo, idesc, flags & 1u, &sm.empty[s]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint2 raw = nxt;
+        if (i + h + 1 < nchunks) nxt = sm.sched[i + h + 1];
+        raw.x = __shfl_sync(0xffffffffu, raw.x, 0);  // warp-uniform by construction; now also to the compiler
+        raw.y = __shfl_sync(0xffffffffu, raw.y, 0);
+        const uint32_t flags = (raw.y >> 20) & 63u;
+        const uint32_t kind = raw.x >> 29;
+        if (flags & 16u) {  // first centre chunk of a GEMM: the previous epilogue has finished the operand in TMEM
+          mbar_wait(&sm.cfull, cph);
+          cph ^= 1u;
+          tc_fence_after();
+        }
+        if (lane == 0) TC_TRACE(0, i + h);
+        const uint32_t idesc = idesc0 | (((p.debug & 16) ? 2u : ((raw.x >> 24) & 31u)) << 17);  // N >> 3 = w_rows / 8
+        const uint32_t d = tmem_base + (((raw.y >> 15) & 31u) << 4);          // d_col
+        const uint32_t a_lo = ring_lo + (uint32_t)((st * stage_bytes + h * slot_bytes) >> 4);
+        const uint32_t b_lo = a_lo + (uint32_t)(a_bytes >> 4);
+        const uint32_t kc = (raw.y >> 9) & 31u;
+        if (p.debug & 32) {
+        } else if (kind == A_TMEM) {
+          umma_f16_ts_kblock_nc(d, tmem_base + COL_A + kc * 32u, b_lo, idesc, flags & 1u);
+        } else if (kind == A_REUSE) {
+          // the operand the epilogue wrote for nin_out's first quarter stays in that quarter's slots
+          umma_f16_kblock_nc(d, kc ? reuse_lo1 : reuse_lo0, b_lo, idesc, flags & 1u);
+        } else {
+          umma_f16_kblock_nc(d, a_lo, b_lo, idesc, flags & 1u);
+        }
+        if (flags & 2u) umma_commit_elect(&sm.acc_full[(flags >> 2) & 3u]);
       }
-      if (flags & 2u) umma_commit_elect(&sm.acc_full[(flags >> 2) & 3u]);
-      if (++s == nst) {
-        s = 0;
+      umma_commit_elect(&sm.empty[st]);  // frees the stage once these eight MMAs have read it
+      if (++st == nst) {
+        st = 0;
         ph ^= 1u;
       }
     }
@@ -485,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       const Chunk ch = unpack_chunk(sm.sched[i]);
       if (ch.a_kind != A_GATHER && ch.a_kind != A_CENTRE) continue;
       if ((seen++ & 3) != gw) continue;
-      const int s = i % nst;
+      const int st = (i >> 1) % nst;
       const int kg = ch.kc * 8 + g;
       int bitpos, off;  // mask bit to test, byte offset from the row's base
       if (ch.a_kind == A_GATHER) {
@@ -504,9 +523,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         bitpos = kg < ch.cin8 ? 27 : 31;
         off = ch.a_tensor * LMT_CELLS * (LMT_ACT * 2) + (ch.ch_off8 + kg) * 16;
       }
-      mbar_wait(&sm.empty[s], ((uint32_t)(i / nst) & 1u) ^ 1u);
+      mbar_wait(&sm.empty[st], ((uint32_t)((i >> 1) / nst) & 1u) ^ 1u);
       if (lane == 0) TC_TRACE(1, i);
-      const uint32_t soff = s * stage_bytes;
+      const uint32_t soff = st * stage_bytes + (i & 1) * slot_bytes;
       if (!(p.debug & 2)) {
 #pragma unroll 4
         for (int m = 0; m < npair; ++m) {
@@ -521,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       // asynchronous completion: the stage's full barrier gets this lane's arrival when its copies have landed, so
       // the warp never blocks on data and every free stage of the ring is in flight (the MMA warp orders the
       // landed generic-proxy writes before its async-proxy reads with fence.proxy.async)
-      cp_async_arrive_noinc(&sm.full[s]);
+      cp_async_arrive_noinc(&sm.full[st]);
       if (lane == 0) TC_TRACE(2, i);
     }
   } else {
@@ -685,20 +704,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
           for (int i = 0; i < 16; ++i) celu(o[i], pp[i], nn);
           if (r < a_rows) {  // rows past the tile's A tile would land in the stage's weights
             const int kg0 = 2 * j, kg1 = 2 * j + 1;
-            sts_a(tiles, (first + (kg0 >> 3)) % nst, stage_bytes, kg0 & 7, r,
+            sts_a(tiles, slot_off(first + (kg0 >> 3)), kg0 & 7, r,
                   make_uint4(pack_h2(pp[0], pp[1]), pack_h2(pp[2], pp[3]), pack_h2(pp[4], pp[5]), pack_h2(pp[6], pp[7])));
-            sts_a(tiles, (first + (kg1 >> 3)) % nst, stage_bytes, kg1 & 7, r,
+            sts_a(tiles, slot_off(first + (kg1 >> 3)), kg1 & 7, r,
                   make_uint4(pack_h2(pp[8], pp[9]), pack_h2(pp[10], pp[11]), pack_h2(pp[12], pp[13]), pack_h2(pp[14], pp[15])));
-            sts_a(tiles, (first + 1) % nst, stage_bytes, 2 + j, r, make_uint4(0, 0, 0, 0));
-            if (j == 0) sts_a(tiles, (first + 1) % nst, stage_bytes, 7, r, make_uint4(0, 0, 0, 0));
+            sts_a(tiles, slot_off(first + 1), 2 + j, r, make_uint4(0, 0, 0, 0));
+            if (j == 0) sts_a(tiles, slot_off(first + 1), 7, r, make_uint4(0, 0, 0, 0));
           }
         }
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
         if (lane < 8) {
-          mbar_arrive(&sm.full[first % nst]);
-          mbar_arrive(&sm.full[(first + 1) % nst]);
+          mbar_arrive(&sm.full[(first >> 1) % nst]);
+          mbar_arrive(&sm.full[((first + 1) >> 1) % nst]);
         }
       }
       mbar_wait(&sm.acc_full[2], 0);
@@ -880,6 +899,7 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   PS_CHECK_ARG(B >= 0 && n_levels >= 0 && temperature > 0.0f);
   PS_CHECK_ARG(plan->n_chunks_body > 0 && plan->n_chunks_total >= plan->n_chunks_body);
   PS_CHECK_ARG(plan->n_chunks_total <= TC_MAX_CHUNKS);
+  PS_CHECK_ARG(plan->n_chunks_body % 2 == 0 && plan->n_chunks_total % 2 == 0);  // two chunks per ring stage
   if (B == 0 || n_levels == 0) return PS_OK;
   PS_CHECK_ARG(rows_dev && level_offsets_host && first_b_level >= 0 && first_b_level <= n_levels);
   PS_CHECK_ARG(uniforms || logits_out);  // sampling needs the uniform numbers

@@ -221,6 +221,57 @@ __device__ __forceinline__ void umma_f16_ts_kblock(uint32_t tmem_d, uint32_t tme
       "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128), "r"(smem_u32(commit_bar))
       : "memory");
 }
+// the same two K blocks without the trailing commit (the caller commits once per ring stage)
+__device__ __forceinline__ void umma_f16_kblock_nc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_kblock_nc(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt;\n\t"
+      ".reg .b64 db;\n\t"
+      ".reg .b32 ta;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b32 ta, %1;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pa;\n\t"
+      "add.u32 ta, ta, 8;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+      "add.u32 ta, ta, 8;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+      "add.u32 ta, ta, 8;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, pt;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
 // whole warp, one elected lane commits
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(

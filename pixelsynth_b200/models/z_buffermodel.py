@@ -216,8 +216,76 @@ class ZbufferModelPts(nn.Module):
         loss = {}  # the reference computes loss_function(gen_img, gen_img) here and discards it (:412-414)
         return loss, outputs
 
+    # -- z_buffermodel.py:421-592 ---------------------------------------------------------------
+    def _splits(self, direction):
+        n = int(_get(self.opt, "num_split", 1))
+        if direction in ("S", "C"):
+            return n * 2
+        if direction in ("U", "D", "UL", "UR", "DR", "DL"):
+            return max(n // 2, 1)
+        return n
+
+    def _scene_views(self, direction, num_split, sequential):
+        """(numerator of the target pose, kind) in rendering order.  Non-sequential outpainting jumps to the far pose
+        first ('far': the source camera is the input view, or the pose the previous direction ended on) and then
+        walks back through the poses in between; sequential outpainting walks outwards from the input view."""
+        if sequential:
+            return [(i, "first" if i == 0 else "step") for i in range(num_split + 1)]
+        return [(num_split, "far")] + [(i, "step") for i in reversed(range(num_split))]
+
+    def forward_scene(self, batch, netD=None, noise=None, uniforms=None):
+        """gen_scene: a sweep of views per direction over ONE growing point cloud.  Every rendered view is fed back as
+        the next source image; only the pixels a view had to outpaint are appended to the cloud
+        (PtsManipulator.forward_justpts_cumulative).  Batch size 1, as in the reference."""
+        K, K_inv, input_RT, input_RTinv, input_img = self.process_batch(batch)
+        if input_img.shape[0] != 1:
+            raise ValueError("gen_scene renders one image at a time (the reference's cameras are built for batch 1)")
+        if _get(self.opt, "no_outpainting", False):
+            raise NotImplementedError("no_outpainting (3-channel decoder, SynSin baseline) is not the shipped configuration")
+        min_z, max_z = float(_get(self.opt, "min_z")), float(_get(self.opt, "max_z"))
+        sequential = bool(_get(self.opt, "sequential_outpainting", False))
+        outputs = {"InputImg": input_img}
+        current_img, cloud, feats, last_bg, last_out_inv = input_img, None, None, None, None
+        last_num, last_dir = None, None
+        self.last_scene = []
+        gen_img = input_img
+        for direction in _get(self.opt, "directions"):
+            num_split = self._splits(direction)
+            for num, kind in self._scene_views(direction, num_split, sequential):
+                if kind in ("far", "first"):
+                    if last_num is not None:
+                        src_inv, src_rt = self.get_rt_from_rot(last_dir, input_RT, last_num, num_split)
+                    else:
+                        src_inv, src_rt = input_RTinv, input_RT
+                else:
+                    src_inv, src_rt = self.get_rt_from_rot(direction, input_RT, last_num, num_split)
+                dst_inv, dst_rt = self.get_rt_from_rot(direction, input_RT, num, num_split)
+                depth = self.pts_regressor.forward(current_img, min_z, max_z)
+                gen_fs, bg, new_cloud, new_feats = self.pts_transformer.forward_justpts_cumulative(
+                    current_img, depth, K, K_inv, src_rt.contiguous(), src_inv.contiguous(), dst_rt.contiguous(),
+                    dst_inv.contiguous(), cloud, feats, last_bg, last_out_inv)
+                _, order, words, sample_mask = self.get_masks_for_batch(dst_rt, src_inv, bg)
+                self._prepared = None
+                codes = self.vqvae.encode_top(gen_fs)
+                gen_img = self.get_best_sample(order, words, sample_mask, codes, bg, gen_fs, netD, input_img, noise, uniforms)
+                self.last_scene.append(dict(direction=direction, num=num, src=current_img, depth=depth, src_rt=src_rt,
+                                            src_inv=src_inv, dst_rt=dst_rt, dst_inv=dst_inv, prior_cloud=cloud,
+                                            prior_feats=feats, prior_bg=last_bg, prior_out_inv=last_out_inv, gen_fs=gen_fs,
+                                            background_mask=bg, cloud=new_cloud))
+                tag = "%s_%d" % (direction, num)
+                outputs["PredImg_" + tag] = gen_img
+                outputs["FeaturesImg_" + tag] = gen_fs
+                if kind == "far" or (sequential and num == num_split):
+                    outputs["PredDepthImg_" + tag] = depth
+                    outputs["ForegroundImg_" + tag] = (~bg).repeat(input_img.shape[0], 1, 1, 1).float()
+                    last_dir = direction
+                current_img, cloud, feats, last_bg, last_out_inv, last_num = gen_img, new_cloud, new_feats, bg, dst_inv, num
+        return {}, outputs
+
     def forward(self, batch, netD=None, **kw):
         setting = _get(self.opt, "model_setting")
         if setting == "gen_scene":
-            raise NotImplementedError("gen_scene (cumulative cloud sweep) is a 'next' row of SURVEY.md 8f")
+            return self.forward_scene(batch, netD, **kw)
+        if setting == "gen_two_imgs":
+            raise NotImplementedError("gen_two_imgs (the consistency evaluation's two-view mode) is evaluation code, out of scope")
         return self.forward_image(batch, netD, **kw)

@@ -86,3 +86,48 @@ def test_gen_img_direction(model):
         assert model.last["sample_mask"].sum() > 50
     finally:
         model.opt.model_setting = "gen_paired_img"
+
+
+def test_gen_scene_sweep(model, oracle):
+    """gen_scene (z_buffermodel.py:421-592): a short sweep over the growing point cloud.  Keys and shapes follow the
+    reference; the last view's cumulative splat is recomputed by the oracle from what the model recorded going in."""
+    from util import pack_mats
+
+    model.opt.model_setting = "gen_scene"
+    model.opt.directions, model.opt.num_split, model.opt.sequential_outpainting = ["L"], 2, False
+    try:
+        batch = make_batch(1, "identity")
+        g = torch.Generator().manual_seed(7)
+        _, out = model.forward(batch, noise=torch.randn(16, 1, 20, generator=g), uniforms=torch.rand(1, 1024, generator=g))
+        torch.cuda.synchronize()
+        # far view first, then the views in between back to the input pose
+        assert [s["num"] for s in model.last_scene] == [2, 1, 0]
+        for k in ("InputImg", "PredImg_L_2", "PredImg_L_1", "PredImg_L_0", "FeaturesImg_L_2", "FeaturesImg_L_0",
+                  "PredDepthImg_L_2", "ForegroundImg_L_2"):
+            assert k in out, k
+        for i in range(3):
+            img = out["PredImg_L_%d" % i]
+            assert img.shape == (1, 3, 256, 256) and torch.isfinite(img).all() and img.abs().max() <= 1 + 1e-6
+        # the cloud grows by exactly the pixels the previous view had to outpaint
+        P = 256 * 256
+        sizes = [s["cloud"].shape[2] for s in model.last_scene]
+        bgs = [int(s["background_mask"].sum()) for s in model.last_scene]
+        assert sizes[0] == P and sizes[1] == P + bgs[0] and sizes[2] == P + bgs[0] + bgs[1] and bgs[0] > 0
+        # last view through the oracle: new pixels (masked by the previous view's background) + the prior cloud
+        s = model.last_scene[-1]
+        f = lambda t: t.detach().float().cpu().numpy()
+        K = f(batch["cameras"][0]["K"])
+        Kinv = f(batch["cameras"][0]["Kinv"])
+        mats = pack_mats(K, Kinv, f(s["src_rt"]), f(s["src_inv"]), f(s["dst_rt"]), f(s["dst_inv"]))
+        pts_n, _ = oracle.project(f(s["depth"]), mats, 256, want_xyproj=True)
+        sel = f(s["prior_bg"]).reshape(-1).astype(bool)
+        mats3 = np.ascontiguousarray(np.stack([K.reshape(1, 16), f(s["dst_rt"]).reshape(1, 16), f(s["prior_out_inv"]).reshape(1, 16)], 1))
+        pts_o, _ = oracle.project_cloud(f(s["prior_cloud"]), mats3)
+        pts_c = np.concatenate([pts_n[:, sel], pts_o], 1)
+        feat_c = np.concatenate([f(s["src"]).reshape(1, 3, -1)[:, :, sel], f(s["prior_feats"])], 2)
+        radius = 4.0 / 256 * 2.0
+        idx, _, d2 = oracle.rasterize(pts_c, 256, 128, radius)
+        np.testing.assert_allclose(f(s["gen_fs"]), oracle.composite(idx, d2, feat_c, radius), rtol=0, atol=2e-6)
+        assert np.array_equal(s["background_mask"].cpu().numpy(), oracle.bgmask(idx, 13))
+    finally:
+        model.opt.model_setting = "gen_paired_img"

@@ -186,3 +186,54 @@ def test_module_mirror_forward_justpts(ops, oracle):
     assert np.array_equal(bg.cpu().numpy(), ref["bg"])
     sampler = pm.project_pts(dev(depth).view(B, 1, -1), *cams)
     assert np.array_equal(sampler.permute(0, 2, 1).cpu().numpy(), ref["pts"])
+
+
+def test_cumulative_cloud_two_views(ops, oracle):
+    """S2c: PtsManipulator.forward_justpts_cumulative (z_buffer_manipulator.py:184-266) over two consecutive views of
+    one image, as forward_scene drives it: the first view splats the source grid and returns the pre-division cloud;
+    the second appends only the pixels the first view left as background (newly outpainted content) to the prior
+    cloud re-expressed in the new camera.  Clouds and masks bit-exact, image within ATOL_OUT."""
+    from pixelsynth_b200.models.projection.z_buffer_manipulator import PtsManipulator
+    from util import demo_cameras, pack_mats
+
+    W, B, Kpp = 64, 1, 128
+    radius = 4.0 / W * 2.0
+    opt = types.SimpleNamespace(splatter="xyblending", learn_default_feature=True, radius=4.0, pp_pixel=Kpp, rad_pow=2,
+                                tau=1.0, accumulation="alphacomposite", background_smoothing_kernel_size=13)
+    pm = PtsManipulator(W, C=3, opt=opt).cuda()
+    depth1, feat1, _ = synthetic_view(B, W, kind="translate", seed=21, depth_mode="smooth")
+    depth2, feat2, _ = synthetic_view(B, W, kind="translate", seed=22, depth_mode="smooth")
+    K, Kinv, RT1, RT1inv, RT2, RT2inv = demo_cameras(B, "translate", 21, views=[2])
+    _, _, _, _, RT3, RT3inv = demo_cameras(B, "translate", 21, views=[3])
+    RT2[:, 0, 3] += 0.6  # push part of the first view out of frame so it leaves a background band
+    RT2inv = np.linalg.inv(RT2).astype(np.float32)
+
+    # ---- view 1: no prior cloud ----
+    g = [dev(m) for m in (K, Kinv, RT1, RT1inv, RT2, RT2inv)]
+    res1, bg1, cloud1, src1 = pm.forward_justpts_cumulative(dev(feat1), dev(depth1), *g, None, None, None, None)
+    pts_a, xyp_a = oracle.project(depth1, pack_mats(K, Kinv, RT1, RT1inv, RT2, RT2inv), W, want_xyproj=True)
+    idx_a, _, d2_a = oracle.rasterize(pts_a, W, Kpp, radius)
+    out_a = oracle.composite(idx_a, d2_a, feat1.reshape(B, 3, -1), radius)
+    bg_a = oracle.bgmask(idx_a, 13)
+    assert np.array_equal(cloud1.cpu().numpy(), xyp_a)
+    assert np.array_equal(bg1.cpu().numpy(), bg_a) and 0 < bg_a.sum() < bg_a.size
+    np.testing.assert_allclose(res1.cpu().numpy(), out_a, rtol=0, atol=ATOL_OUT)
+    assert np.array_equal(src1.cpu().numpy(), feat1.reshape(B, 3, -1))
+
+    # ---- view 2: the "outpainted" image (feat2, depth2) seen from camera 2, moved to camera 3 ----
+    g2 = [dev(m) for m in (K, Kinv, RT2, RT2inv, RT3, RT3inv)]
+    res2, bg2, cloud2, src2 = pm.forward_justpts_cumulative(dev(feat2), dev(depth2), *g2, cloud1, src1, bg1, dev(RT2inv))
+    sel = bg_a.reshape(B, -1)[0]
+    pts_n, xyp_n = oracle.project(depth2, pack_mats(K, Kinv, RT2, RT2inv, RT3, RT3inv), W, want_xyproj=True)
+    mats3 = np.ascontiguousarray(np.stack([K.reshape(B, 16), RT3.reshape(B, 16), RT2inv.reshape(B, 16)], 1))
+    pts_o, xyp_o = oracle.project_cloud(xyp_a, mats3)
+    pts_c = np.concatenate([pts_n[:, sel], pts_o], 1)
+    xyp_c = np.concatenate([xyp_n[:, :, sel], xyp_o], 2)
+    feat_c = np.concatenate([feat2.reshape(B, 3, -1)[:, :, sel], feat1.reshape(B, 3, -1)], 2)
+    idx_c, _, d2_c = oracle.rasterize(pts_c, W, Kpp, radius)
+    out_c = oracle.composite(idx_c, d2_c, feat_c, radius)
+    assert cloud2.shape == (B, 4, int(sel.sum()) + W * W)
+    assert np.array_equal(cloud2.cpu().numpy(), xyp_c)
+    assert np.array_equal(src2.cpu().numpy(), feat_c)
+    assert np.array_equal(bg2.cpu().numpy(), oracle.bgmask(idx_c, 13))
+    np.testing.assert_allclose(res2.cpu().numpy(), out_c, rtol=0, atol=ATOL_OUT)

@@ -20,6 +20,7 @@
 // main loop of tile i + 1.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -31,6 +32,10 @@ constexpr int BM = 128;  // output pixels per tile (UMMA M)
 constexpr int BK = 64;   // channels per K step (128 bytes of bf16 = one swizzle row)
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int CONV_MAX_STAGES = 8;
+// halo mode: tile = 8 x 16 output pixels; the halo tile is 18 rows of 16 pixels (10 used: the pitch is a multiple of 8
+// pixels so that every 8-pixel row group of a shifted window has the same swizzle phase) x 64 channels
+constexpr int HALO_W = 16, HALO_H = 18;
+constexpr int HALO_BYTES = HALO_W * HALO_H * BK * 2;  // 36 KB
 
 struct ConvKernelParams {
   // tile geometry: TW * TH * TN == 128
@@ -44,6 +49,9 @@ struct ConvKernelParams {
   int wrow[2][16];  // first weight row (of the packed [rows][Cin_pad] matrix) of each tap
   int BN;           // output channels per CTA (multiple of 16, <= 256)
   int stages;
+  int halo;         // 3x3 stride-1 mode: input 0's taps are read in place from one (TH+2) x 16-pixel halo tile per chunk
+  int a_stage_bytes;  // A part of a ring stage (0 when no k-iteration stages an A tile)
+  int debug;
   // epilogue
   int Cout;  // real output channels (columns >= Cout are dropped)
   const float* bias;
@@ -106,20 +114,24 @@ __device__ __forceinline__ void store_block32(const float* f, const float* sc, c
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                      const __grid_constant__ CUtensorMap mapW, const ConvKernelParams p) {
+                      const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH,
+                      const ConvKernelParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform to the compiler as well
   const int BN = p.BN;
   const int BNp = (BN + 31) & ~31;  // TMEM columns per accumulator buffer
-  const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
-  // carve: [stages x (A | B)] then barriers
-  unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = p.a_stage_bytes + BN * BK * 2;
+  // carve: [2 halo tiles (halo mode)] [stages x (A | B)] then barriers
+  unsigned char* halo_tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = halo_tiles + (p.halo ? 2 * HALO_BYTES : 0);
   uint64_t* full_bar = (uint64_t*)(tiles + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* acc_full = empty_bar + p.stages;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  uint64_t* halo_full = acc_empty + 2;
+  uint64_t* halo_empty = halo_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(halo_empty + 2);
   const int kiters = p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1];
   const uint32_t ncols = 2 * BNp <= 32 ? 32u : (2 * BNp <= 64 ? 64u : (2 * BNp <= 128 ? 128u : (2 * BNp <= 256 ? 256u : 512u)));
 
@@ -127,6 +139,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapW);
     if (p.ntaps[1]) tma_prefetch_desc(&mapA1);
+    if (p.halo) tma_prefetch_desc(&mapH);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -137,6 +150,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       for (int b = 0; b < 2; ++b) {
         mbar_init(&acc_full[b], 1);
         mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+        mbar_init(&halo_full[b], 1);
+        mbar_init(&halo_empty[b], 1);
       }
       mbar_fence_init();
     }
@@ -151,13 +166,31 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int it = 0;
+      int it = 0, hit = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
         const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
         const int ox0 = tx * p.TW, oy0 = ty * p.TH, n0 = tn * p.TN, ncol0 = cb * BN;
         for (int src = 0; src < 2; ++src) {
           const CUtensorMap* mA = src ? &mapA1 : &mapA0;
+          if (src == 0 && p.halo) {
+            // one halo tile per 64-channel chunk, then the nine weight tiles that are multiplied against it
+            for (int kc = 0; kc < p.kchunks[0]; ++kc, ++hit) {
+              const int hb = hit & 1;
+              mbar_wait(&halo_empty[hb], (((uint32_t)hit >> 1) & 1u) ^ 1u);
+              mbar_expect_tx(&halo_full[hb], (uint32_t)HALO_BYTES);
+              tma_load_4d(&mapH, &halo_full[hb], halo_tiles + (size_t)hb * HALO_BYTES, kc * BK, ox0 - 1, oy0 - 1, n0);
+              for (int t = 0; t < p.ntaps[0]; ++t, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                unsigned char* a = tiles + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], (uint32_t)(BN * BK * 2));
+                tma_load_2d(&mapW, &full_bar[s], a + p.a_stage_bytes, kc * BK, p.wrow[0][t] + ncol0);
+              }
+            }
+            continue;
+          }
           for (int t = 0; t < p.ntaps[src]; ++t) {
             const int ix0 = ox0 * p.stride + p.dx[src][t];
             const int iy0 = oy0 * p.stride + p.dy[src][t];
@@ -166,9 +199,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
               const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
               mbar_wait(&empty_bar[s], ph ^ 1u);
               unsigned char* a = tiles + (size_t)s * stage_bytes;
-              mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+              mbar_expect_tx(&full_bar[s], (uint32_t)(A_STAGE_BYTES + BN * BK * 2));
               tma_load_4d(mA, &full_bar[s], a, kc * BK, ix0, iy0, n0);
-              tma_load_2d(&mapW, &full_bar[s], a + A_STAGE_BYTES, kc * BK, p.wrow[src][t] + ncol0);
+              tma_load_2d(&mapW, &full_bar[s], a + p.a_stage_bytes, kc * BK, p.wrow[src][t] + ncol0);
             }
           }
         }
@@ -178,18 +211,46 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     // ===== MMA issuer: whole warp, warp-uniform operands, one elected lane issues (tc05.cuh: umma_f16_kblock) =====
     const uint32_t idesc = umma_idesc_bf16(BN);
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
-    int s = 0, lt = 0;
+    int s = 0, lt = 0, hit = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       mbar_wait(&acc_empty[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(buf * BNp);
-      for (int it = 0; it < kiters; ++it) {
+      int it = 0;
+      if (p.halo) {
+        for (int kc = 0; kc < p.kchunks[0]; ++kc, ++hit) {
+          const int hb = hit & 1;
+          mbar_wait(&halo_full[hb], ((uint32_t)hit >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t halo_addr = smem_u32(halo_tiles + (size_t)hb * HALO_BYTES);
+          for (int t = 0; t < p.ntaps[0]; ++t, ++it) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            // window shifted by the tap: starts (1+dy) halo rows and (1+dx) pixels in; 8-pixel row groups are one
+            // halo row (16 pixels = 2048 bytes) apart.  The 128-byte swizzle is a function of the shared-memory
+            // address bits, for TMA's writes and the MMA's reads alike, so a start row that is not a multiple of 8
+            // needs nothing else (descriptor base offset 0; measured: a non-zero base offset reads the wrong chunks).
+            const uint32_t r0 = (uint32_t)((1 + p.dy[0][t]) * HALO_W + 1 + p.dx[0][t]);
+            const uint32_t a_addr = halo_addr + r0 * 128u;
+            const uint32_t a_lo = umma_desc_lo(a_addr);
+            const uint32_t a_hi = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(p.a_stage_bytes >> 4);
+            umma_f16_kblock_ahi(d, a_lo, a_hi, b_lo, idesc, it ? 1u : 0u, &empty_bar[s]);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+          umma_commit_elect(&halo_empty[hb]);  // the halo tile is free once its nine taps have been multiplied
+        }
+      }
+      for (; it < kiters; ++it) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4);
-        umma_f16_kblock(d, a_lo, a_lo + (A_STAGE_BYTES >> 4), idesc, it ? 1u : 0u, &empty_bar[s]);
+        umma_f16_kblock(d, a_lo, a_lo + (uint32_t)(p.a_stage_bytes >> 4), idesc, it ? 1u : 0u, &empty_bar[s]);
         if (++s == p.stages) {
           s = 0;
           ph ^= 1u;
@@ -396,6 +457,21 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   while (TH > 1 && TH / 2 >= d->Hout) TH /= 2;
   if (TH > 8 && d->Hout >= 8 && TW == 16) TH = 8;
   int TN = BM / (TW * TH);
+  // halo mode: stride-1 convolution whose first input's taps all lie in the 3x3 window, on images that fill the
+  // 8 x 16 tile.  The window of every tap is then read in place from one halo tile per 64-channel chunk instead of
+  // being fetched once per tap (input traffic / 9 * 2.25).
+  const int dbg = getenv("PS_CONV_DEBUG") ? atoi(getenv("PS_CONV_DEBUG")) : 0;
+  bool halo = d->stride == 1 && d->Wout >= 8 && d->Hout >= 16 && !(dbg & 2);
+  for (int t = 0; t < d->in[0].ntaps; ++t)
+    halo = halo && d->in[0].dy[t] >= -1 && d->in[0].dy[t] <= 1 && d->in[0].dx[t] >= -1 && d->in[0].dx[t] <= 1;
+  halo = halo && d->in[0].ntaps > 1;
+  if (halo) {
+    TW = 8;
+    TH = 16;
+    TN = 1;
+  }
+  p.halo = halo ? 1 : 0;
+  p.debug = dbg;
   p.TW = TW;
   p.TH = TH;
   p.TN = TN;
@@ -410,12 +486,14 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   int BN = d->cout_pad <= 256 ? d->cout_pad : 128;
   PS_CHECK_ARG(d->cout_pad % BN == 0);
   p.BN = BN;
-  const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
+  // a ring stage carries an A tile only if some k-iteration stages one (not input 0 in halo mode)
+  p.a_stage_bytes = (!halo || d->in[1].ntaps > 0) ? A_STAGE_BYTES : 0;
+  const int stage_bytes = p.a_stage_bytes + BN * BK * 2;
   // one persistent CTA per SM: as many ring stages as ~200 KB of shared memory hold
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (200 * 1024 - (halo ? 2 * HALO_BYTES : 0)) / stage_bytes;
   stages = stages > CONV_MAX_STAGES ? CONV_MAX_STAGES : (stages < 2 ? 2 : stages);
   p.stages = stages;
-  CUtensorMap mapA[2], mapW;
+  CUtensorMap mapA[2], mapW, mapH;
   memset(mapA, 0, sizeof(mapA));
   int wrows = 0;
   for (int s = 0; s < 2; ++s) {
@@ -438,6 +516,12 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   if (p.ntaps[1] == 0) mapA[1] = mapA[0];
   int rc = make_w_map(&mapW, d->weights, d->w_rows, d->w_cin_pad, BN);
   if (rc != PS_OK) return rc;
+  mapH = mapA[0];
+  if (halo) {
+    const ps_conv_input& in = d->in[0];
+    rc = make_act_map(&mapH, in.ptr, d->N, in.H, in.W, in.C, in.cstride, HALO_W, HALO_H, 1, 1);
+    if (rc != PS_OK) return rc;
+  }
   p.Cout = d->Cout;
   p.bias = d->bias;
   p.residual = (const __nv_bfloat16*)d->residual;
@@ -461,7 +545,7 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.out_py = d->out_py;
   p.out_px = d->out_px;
 
-  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+  const size_t smem_bytes = 1024 + (halo ? 2 * HALO_BYTES : 0) + (size_t)stages * stage_bytes + (2 * stages + 8) * sizeof(uint64_t) + 16;
   static thread_local int attr_dev = -1;
   static thread_local int sms = 148;
   int dev = 0;
@@ -475,7 +559,7 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.total_tiles = p.tiles_spatial * (d->cout_pad / BN);
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   PS_TIME_BEGIN("conv_igemm_kernel", (cudaStream_t)stream);
-  conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, (cudaStream_t)stream>>>(mapA[0], mapA[1], mapW, p);
+  conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, (cudaStream_t)stream>>>(mapA[0], mapA[1], mapW, mapH, p);
   PS_TIME_END((cudaStream_t)stream);
   PS_LAUNCHED();
   return PS_OK;

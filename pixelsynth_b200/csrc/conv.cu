@@ -13,9 +13,9 @@
 // accumulated into the same tile (the decoder's 1x1 skip convolution, blocks.py:43,65-66).
 //
 // Persistent kernel, one CTA per SM, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Warp roles (192
-// threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (each reads its
-// 32-lane TMEM quadrant with tcgen05.ld, applies bias / residual / per-sample scale+shift / activation and writes up
-// to two NHWC outputs).  The smem ring of `stages` stages (full/empty mbarriers) runs on across tiles, and the
+// threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue (two warps per
+// 32-lane TMEM quadrant, each taking every other 32-column block: tcgen05.ld, bias / residual / per-sample
+// scale+shift / activation, up to two NHWC outputs; the epilogue is a chain of dependent loads, so it wants warps).  The smem ring of `stages` stages (full/empty mbarriers) runs on across tiles, and the
 // accumulator is double buffered in TMEM (acc_full / acc_empty mbarriers), so the epilogue of tile i overlaps the
 // main loop of tile i + 1.
 #include <cuda.h>
@@ -27,7 +27,7 @@
 
 namespace ps {
 
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_THREADS = 320;  // producer, MMA issuer, 8 epilogue warps
 constexpr int BM = 128;  // output pixels per tile (UMMA M)
 constexpr int BK = 64;   // channels per K step (128 bytes of bf16 = one swizzle row)
 constexpr int A_STAGE_BYTES = BM * BK * 2;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&acc_full[b], 1);
-        mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+        mbar_init(&acc_empty[b], 8);  // one arrival per epilogue warp
         mbar_init(&halo_full[b], 1);
         mbar_init(&halo_empty[b], 1);
       }
@@ -164,44 +164,76 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0, hit = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
-        const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
-        const int ox0 = tx * p.TW, oy0 = ty * p.TH, n0 = tn * p.TN, ncol0 = cb * BN;
-        for (int src = 0; src < 2; ++src) {
-          const CUtensorMap* mA = src ? &mapA1 : &mapA0;
-          if (src == 0 && p.halo) {
-            // one halo tile per 64-channel chunk, then the nine weight tiles that are multiplied against it
-            for (int kc = 0; kc < p.kchunks[0]; ++kc, ++hit) {
-              const int hb = hit & 1;
-              mbar_wait(&halo_empty[hb], (((uint32_t)hit >> 1) & 1u) ^ 1u);
-              mbar_expect_tx(&halo_full[hb], (uint32_t)HALO_BYTES);
-              tma_load_4d(&mapH, &halo_full[hb], halo_tiles + (size_t)hb * HALO_BYTES, kc * BK, ox0 - 1, oy0 - 1, n0);
-              for (int t = 0; t < p.ntaps[0]; ++t, ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                unsigned char* a = tiles + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full_bar[s], (uint32_t)(BN * BK * 2));
-                tma_load_2d(&mapW, &full_bar[s], a + p.a_stage_bytes, kc * BK, p.wrow[0][t] + ncol0);
+    // ===== TMA producer: the whole warp walks the loop (uniform control flow, incremental ring state); one elected
+    // lane arms the barrier and issues the copies.  Lane t keeps tap t's parameters; a shuffle fetches them. =====
+    const int tl = lane & 15;
+    const int my_dx0 = p.dx[0][tl], my_dy0 = p.dy[0][tl], my_w0 = p.wrow[0][tl];
+    const int my_dx1 = p.dx[1][tl], my_dy1 = p.dy[1][tl], my_w1 = p.wrow[1][tl];
+    const uint32_t w_bytes = (uint32_t)(BN * BK * 2);
+    int s = 0, hit = 0;
+    uint32_t ph = 1;  // parity of the `empty` phase to wait for (passes on a fresh barrier)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
+      const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
+      const int ox0 = tx * p.TW, oy0 = ty * p.TH, n0 = tn * p.TN, ncol0 = cb * BN;
+      for (int src = 0; src < 2; ++src) {
+        const CUtensorMap* mA = src ? &mapA1 : &mapA0;
+        if (src == 0 && p.halo) {
+          // one halo tile per 64-channel chunk, then the nine weight tiles that are multiplied against it
+          for (int kc = 0; kc < p.kchunks[0]; ++kc, ++hit) {
+            const int hb = hit & 1;
+            mbar_wait(&halo_empty[hb], (((uint32_t)hit >> 1) & 1u) ^ 1u);
+            if (elect_one()) {
+              if (p.debug & 8) {
+                mbar_arrive(&halo_full[hb]);
+              } else {
+                mbar_expect_tx(&halo_full[hb], (uint32_t)HALO_BYTES);
+                tma_load_4d(&mapH, &halo_full[hb], halo_tiles + (size_t)hb * HALO_BYTES, kc * BK, ox0 - 1, oy0 - 1, n0);
               }
             }
-            continue;
+            __syncwarp();
+            for (int t = 0; t < p.ntaps[0]; ++t) {
+              const int wr = __shfl_sync(0xffffffffu, my_w0, t);
+              mbar_wait(&empty_bar[s], ph);
+              if (elect_one()) {
+                if (p.debug & 8) {
+                  mbar_arrive(&full_bar[s]);
+                } else {
+                  mbar_expect_tx(&full_bar[s], w_bytes);
+                  tma_load_2d(&mapW, &full_bar[s], tiles + (size_t)s * stage_bytes + p.a_stage_bytes, kc * BK, wr + ncol0);
+                }
+              }
+              __syncwarp();
+              if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+              }
+            }
           }
-          for (int t = 0; t < p.ntaps[src]; ++t) {
-            const int ix0 = ox0 * p.stride + p.dx[src][t];
-            const int iy0 = oy0 * p.stride + p.dy[src][t];
-            for (int kc = 0; kc < p.kchunks[src]; ++kc, ++it) {
-              const int s = it % p.stages;
-              const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-              mbar_wait(&empty_bar[s], ph ^ 1u);
+          continue;
+        }
+        for (int t = 0; t < p.ntaps[src]; ++t) {
+          const int dx = __shfl_sync(0xffffffffu, src ? my_dx1 : my_dx0, t);
+          const int dy = __shfl_sync(0xffffffffu, src ? my_dy1 : my_dy0, t);
+          const int wr = __shfl_sync(0xffffffffu, src ? my_w1 : my_w0, t);
+          const int ix0 = ox0 * p.stride + dx;
+          const int iy0 = oy0 * p.stride + dy;
+          for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+            mbar_wait(&empty_bar[s], ph);
+            if (elect_one()) {
               unsigned char* a = tiles + (size_t)s * stage_bytes;
-              mbar_expect_tx(&full_bar[s], (uint32_t)(A_STAGE_BYTES + BN * BK * 2));
-              tma_load_4d(mA, &full_bar[s], a, kc * BK, ix0, iy0, n0);
-              tma_load_2d(&mapW, &full_bar[s], a + p.a_stage_bytes, kc * BK, p.wrow[src][t] + ncol0);
+              if (p.debug & 8) {
+                mbar_arrive(&full_bar[s]);
+              } else {
+                mbar_expect_tx(&full_bar[s], (uint32_t)A_STAGE_BYTES + w_bytes);
+                tma_load_4d(mA, &full_bar[s], a, kc * BK, ix0, iy0, n0);
+                tma_load_2d(&mapW, &full_bar[s], a + p.a_stage_bytes, kc * BK, wr + ncol0);
+              }
+            }
+            __syncwarp();
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
             }
           }
         }
@@ -211,6 +243,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     // ===== MMA issuer: whole warp, warp-uniform operands, one elected lane issues (tc05.cuh: umma_f16_kblock) =====
     const uint32_t idesc = umma_idesc_bf16(BN);
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
+    const int my_r0 = (1 + p.dy[0][lane & 15]) * HALO_W + 1 + p.dx[0][lane & 15];  // lane t: tap t's start row in the halo tile
     int s = 0, lt = 0, hit = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -232,12 +265,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             // halo row (16 pixels = 2048 bytes) apart.  The 128-byte swizzle is a function of the shared-memory
             // address bits, for TMA's writes and the MMA's reads alike, so a start row that is not a multiple of 8
             // needs nothing else (descriptor base offset 0; measured: a non-zero base offset reads the wrong chunks).
-            const uint32_t r0 = (uint32_t)((1 + p.dy[0][t]) * HALO_W + 1 + p.dx[0][t]);
+            const uint32_t r0 = (uint32_t)__shfl_sync(0xffffffffu, my_r0, t);
             const uint32_t a_addr = halo_addr + r0 * 128u;
             const uint32_t a_lo = umma_desc_lo(a_addr);
             const uint32_t a_hi = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
             const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(p.a_stage_bytes >> 4);
-            umma_f16_kblock_ahi(d, a_lo, a_hi, b_lo, idesc, it ? 1u : 0u, &empty_bar[s]);
+            if (p.debug & 4) umma_commit_elect(&empty_bar[s]);
+            else umma_f16_kblock_ahi(d, a_lo, a_hi, b_lo, idesc, it ? 1u : 0u, &empty_bar[s]);
             if (++s == p.stages) {
               s = 0;
               ph ^= 1u;
@@ -250,7 +284,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4);
-        umma_f16_kblock(d, a_lo, a_lo + (uint32_t)(p.a_stage_bytes >> 4), idesc, it ? 1u : 0u, &empty_bar[s]);
+        if (p.debug & 4) umma_commit_elect(&empty_bar[s]);
+        else umma_f16_kblock(d, a_lo, a_lo + (uint32_t)(p.a_stage_bytes >> 4), idesc, it ? 1u : 0u, &empty_bar[s]);
         if (++s == p.stages) {
           s = 0;
           ph ^= 1u;
@@ -259,8 +294,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       umma_commit_elect(&acc_full[buf]);  // accumulator complete
     }
   } else {
-    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
+    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 and the 32-column blocks of parity (w-2)/4 =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;  // tile row = output pixel
     const int nl = m / (p.TH * p.TW);
     const int rem = m - nl * (p.TH * p.TW);
@@ -277,15 +313,23 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BNp);
       mbar_wait(&acc_full[buf], ((uint32_t)lt >> 1) & 1u);
       tc_fence_after();
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN && !(p.debug & 16); c0 += 64) {
         uint32_t v[32];
-        tmem_ld32(tbase + (uint32_t)c0, v);
         const int cbase = ncol0 + c0;
-        if (!valid || cbase >= p.Cout) continue;
+        const bool full = cbase + 32 <= p.Cout && (p.Cout & 3) == 0;
+        const bool live = valid && cbase < p.Cout;
+        // the residual comes from L2 / HBM: ask for it before waiting for the accumulator
+        uint4 rv[4];
+        if (live && full && p.residual) {
+          const uint4* r = reinterpret_cast<const uint4*>(p.residual + pixel * p.res_cstride + cbase);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[j] = __ldg(r + j);
+        }
+        tmem_ld32(tbase + (uint32_t)c0, v);
+        if (!live) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const bool full = cbase + 32 <= p.Cout && (p.Cout & 3) == 0;
         if (full) {
           if (p.bias) {
 #pragma unroll
@@ -298,10 +342,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             }
           }
           if (p.residual) {
-            const uint4* r = reinterpret_cast<const uint4*>(p.residual + pixel * p.res_cstride + cbase);
-            uint4 rv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rv[j] = __ldg(r + j);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[j]);

@@ -103,6 +103,18 @@ __device__ __forceinline__ void bulk_load_elect(void* dst, const void* src, uint
       "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// whole warp converged: true in exactly one lane
+__device__ __forceinline__ bool elect_one() {
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, pe;\n\t"
+      "}"
+      : "=r"(r));
+  return r != 0;
+}
 // 16-byte Ampere-style async copy with zero fill (src_bytes = 0 or 16)
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"((uint64_t)src), "r"(src_bytes) : "memory");

@@ -32,10 +32,12 @@ constexpr int BM = 128;  // output pixels per tile (UMMA M)
 constexpr int BK = 64;   // channels per K step (128 bytes of bf16 = one swizzle row)
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int CONV_MAX_STAGES = 8;
-// halo mode: tile = 8 x 16 output pixels; the halo tile is 18 rows of 16 pixels (10 used: the pitch is a multiple of 8
-// pixels so that every 8-pixel row group of a shifted window has the same swizzle phase) x 64 channels
-constexpr int HALO_W = 16, HALO_H = 18;
-constexpr int HALO_BYTES = HALO_W * HALO_H * BK * 2;  // 36 KB
+// halo mode: tile = 8 x 16 output pixels; the halo tile is 18 rows of 10 pixels x 64 channels.  The 128-byte swizzle
+// is a function of the shared-memory address for TMA and MMA alike, so the 8-pixel row groups of a shifted window may
+// start on any 128-byte row.
+constexpr int HALO_W = 10, HALO_H = 18;
+constexpr int HALO_LOAD_BYTES = HALO_W * HALO_H * BK * 2;         // 23040 bytes per TMA box
+constexpr int HALO_BYTES = (HALO_LOAD_BYTES + 1023) / 1024 * 1024;  // buffer stride
 
 struct ConvKernelParams {
   // tile geometry: TW * TH * TN == 128
@@ -85,30 +87,44 @@ __device__ __forceinline__ float apply_act(float v, int act, const float* ap) {
 
 // y[0..32) = act(f * scale + shift) -> 64 bytes of bf16 at dst (16-byte aligned); the activation is a compile-time
 // constant here so the 32-wide loop carries no switch
+// Warp-private staging tile: 32 rows x 64 bytes (one 32-channel bf16 block per output pixel).  A lane owns a row when
+// it computes, and a 16-byte chunk of every eighth row when it talks to global memory (four lanes cover a row's
+// 64 contiguous bytes, so a warp instruction touches 8 lines instead of 32).  Chunk c of row r lives at chunk
+// c ^ ((r >> 1) & 3): both access patterns are then bank-conflict free.
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r, int c) { return base + r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// y[0..32) = act(f * scale + shift) as bf16 into row `lane` of the staging tile; the activation is a compile-time
+// constant here so the 32-wide loop carries no switch
 template <int ACT>
-__device__ __forceinline__ void store_block32(const float* f, const float* sc, const float* sh, const float* ap,
-                                              __nv_bfloat16* dst) {
+__device__ __forceinline__ void stage_block32(const float* f, const float4* sc, const float4* sh, const float* ap,
+                                              uint32_t stage, int lane) {
   float y[32];
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sc) a = __ldg(reinterpret_cast<const float4*>(sc + j));
-    if (sh) b = __ldg(reinterpret_cast<const float4*>(sh + j));
-    y[j] = apply_act(fmaf(f[j], a.x, b.x), ACT, ap);
-    y[j + 1] = apply_act(fmaf(f[j + 1], a.y, b.y), ACT, ap);
-    y[j + 2] = apply_act(fmaf(f[j + 2], a.z, b.z), ACT, ap);
-    y[j + 3] = apply_act(fmaf(f[j + 3], a.w, b.w), ACT, ap);
+  for (int j = 0; j < 8; ++j) {
+    const float4 a = sc[j], b = sh[j];
+    y[4 * j] = apply_act(fmaf(f[4 * j], a.x, b.x), ACT, ap);
+    y[4 * j + 1] = apply_act(fmaf(f[4 * j + 1], a.y, b.y), ACT, ap);
+    y[4 * j + 2] = apply_act(fmaf(f[4 * j + 2], a.z, b.z), ACT, ap);
+    y[4 * j + 3] = apply_act(fmaf(f[4 * j + 3], a.w, b.w), ACT, ap);
   }
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(y[j], y[j + 1]), h1 = __floats2bfloat162_rn(y[j + 2], y[j + 3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(y[j + 4], y[j + 5]), h3 = __floats2bfloat162_rn(y[j + 6], y[j + 7]);
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(y[8 * j], y[8 * j + 1]), h1 = __floats2bfloat162_rn(y[8 * j + 2], y[8 * j + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 4], y[8 * j + 5]), h3 = __floats2bfloat162_rn(y[8 * j + 6], y[8 * j + 7]);
     uint4 w;
     w.x = *reinterpret_cast<uint32_t*>(&h0);
     w.y = *reinterpret_cast<uint32_t*>(&h1);
     w.z = *reinterpret_cast<uint32_t*>(&h2);
     w.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(dst + j) = w;
+    sts128(stage_addr(stage, lane, j), w);
   }
 }
 
@@ -132,6 +148,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
   uint64_t* halo_full = acc_empty + 2;
   uint64_t* halo_empty = halo_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(halo_empty + 2);
+  unsigned char* param_smem = (unsigned char*)(tmem_slot + 4);  // 16-byte aligned: 8 warps x 2 buffers x 40 float4
+  unsigned char* stage_smem = param_smem + 8 * 2 * 40 * 16;      // 8 warps x 2 staging tiles of 2 KB
   const int kiters = p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1];
   const uint32_t ncols = 2 * BNp <= 32 ? 32u : (2 * BNp <= 64 ? 64u : (2 * BNp <= 128 ? 128u : (2 * BNp <= 256 ? 256u : 512u)));
 
@@ -187,7 +205,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
               if (p.debug & 8) {
                 mbar_arrive(&halo_full[hb]);
               } else {
-                mbar_expect_tx(&halo_full[hb], (uint32_t)HALO_BYTES);
+                mbar_expect_tx(&halo_full[hb], (uint32_t)HALO_LOAD_BYTES);
                 tma_load_4d(&mapH, &halo_full[hb], halo_tiles + (size_t)hb * HALO_BYTES, kc * BK, ox0 - 1, oy0 - 1, n0);
               }
             }
@@ -295,56 +313,172 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
   } else {
     // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 and the 32-column blocks of parity (w-2)/4 =====
+    // Work items = (tile, 32-column block).  The per-channel parameters of an item (bias, scale/shift of both outputs)
+    // are the same for every row, so the warp fetches them once -- lane l loads one float4 -- a whole item ahead,
+    // parks them in a warp-private shared-memory buffer and reads them back as broadcasts; the residual rows of the
+    // next item are requested a whole item ahead too.  Nothing on the item's critical path waits for L2.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;  // tile row = output pixel
     const int nl = m / (p.TH * p.TW);
     const int rem = m - nl * (p.TH * p.TW);
     const int my = rem / p.TW, mx = rem % p.TW;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    float4* pbuf = reinterpret_cast<float4*>(param_smem) + (warp - 2) * 2 * 40;
+    const bool shared_params = p.TN == 1 || !(p.per_sample[0] || p.per_sample[1]);
+
+    struct Geom {
+      bool valid;
+      int n, fy, fx, ncol0;
+      size_t pixel;
+    };
+    auto geom = [&](int tile) {
+      Geom g;
       const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
       const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
-      const int oy = ty * p.TH + my, ox = tx * p.TW + mx, n = tn * p.TN + nl, ncol0 = cb * BN;
-      const bool valid = n < p.N && oy < p.Hout && ox < p.Wout;
-      const int fy = oy * p.out_sy + p.out_py, fx = ox * p.out_sx + p.out_px;
-      const size_t pixel = ((size_t)n * p.out_H + fy) * p.out_W + fx;
-      const int buf = lt & 1;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BNp);
-      mbar_wait(&acc_full[buf], ((uint32_t)lt >> 1) & 1u);
-      tc_fence_after();
-      for (int c0 = half * 32; c0 < BN && !(p.debug & 16); c0 += 64) {
-        uint32_t v[32];
-        const int cbase = ncol0 + c0;
-        const bool full = cbase + 32 <= p.Cout && (p.Cout & 3) == 0;
-        const bool live = valid && cbase < p.Cout;
-        // the residual comes from L2 / HBM: ask for it before waiting for the accumulator
-        uint4 rv[4];
-        if (live && full && p.residual) {
-          const uint4* r = reinterpret_cast<const uint4*>(p.residual + pixel * p.res_cstride + cbase);
+      const int oy = ty * p.TH + my, ox = tx * p.TW + mx;
+      g.n = tn * p.TN + nl;
+      g.ncol0 = cb * BN;
+      g.valid = g.n < p.N && oy < p.Hout && ox < p.Wout;
+      g.fy = oy * p.out_sy + p.out_py;
+      g.fx = ox * p.out_sx + p.out_px;
+      g.pixel = ((size_t)g.n * p.out_H + g.fy) * p.out_W + g.fx;
+      return g;
+    };
+    // float4 number idx (0..39) of an item's parameters: [bias | scale0 | shift0 | scale1 | shift1] x 8
+    auto load_param = [&](int idx, int n_tile, int cbase) {
+      const int k = idx >> 3, j = (idx & 7) * 4;
+      const float* src = nullptr;
+      float dflt = 0.f;
+      if (k == 0) {
+        src = p.bias;
+      } else {
+        const int o = (k - 1) >> 1;
+        src = ((k - 1) & 1) ? p.shift[o] : p.scale[o];
+        dflt = ((k - 1) & 1) ? 0.f : 1.f;
+        if (src && p.per_sample[o]) src += (size_t)n_tile * p.Cout;
+      }
+      if (!src) return make_float4(dflt, dflt, dflt, dflt);
+      return __ldg(reinterpret_cast<const float4*>(src + cbase + j));
+    };
+    auto block_full = [&](int cbase) { return cbase + 32 <= p.Cout && (p.Cout & 3) == 0; };
+    auto prefetch_params = [&](int tile, int c0, float4& a, float4& b) {
+      const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
+      const int n_tile = (sp / (p.tiles_x * p.tiles_y)) * p.TN;
+      const int cbase = cb * BN + c0;
+      a = b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (shared_params && block_full(cbase)) {
+        a = load_param(lane, n_tile, cbase);
+        if (lane < 8) b = load_param(lane + 32, n_tile, cbase);
+      }
+    };
+    // lane l talks to global memory for chunk l & 3 of rows 8i + (l >> 2), i = 0..3; the rows' pixel offsets and
+    // validity come from the lanes that own them
+    const int trow = lane >> 2, tchunk = lane & 3;
+    auto prefetch_residual = [&](const Geom& g, int c0, uint4* rv) {
+      const int cbase = g.ncol0 + c0;
+      if (!p.residual || !block_full(cbase) || ((p.res_cstride | cbase) & 7)) return;  // warp-uniform
+      const unsigned vmask = __ballot_sync(0xffffffffu, g.valid);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = __ldg(r + j);
-        }
-        tmem_ld32(tbase + (uint32_t)c0, v);
-        if (!live) continue;
+      for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + trow;
+        const unsigned long long px = __shfl_sync(0xffffffffu, (unsigned long long)g.pixel, r);
+        rv[i] = make_uint4(0, 0, 0, 0);
+        if ((vmask >> r) & 1u)
+          rv[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + px * p.res_cstride + cbase) + tchunk);
+      }
+    };
+    // the staging tile -> global rows, coalesced
+    auto write_out = [&](uint32_t stage, __nv_bfloat16* base, int cstride, const Geom& g) {
+      const unsigned vmask = __ballot_sync(0xffffffffu, g.valid);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + trow;
+        const unsigned long long px = __shfl_sync(0xffffffffu, (unsigned long long)g.pixel, r);
+        const uint4 w = lds128(stage_addr(stage, r, tchunk));
+        if ((vmask >> r) & 1u) *(reinterpret_cast<uint4*>(base + px * cstride) + tchunk) = w;
+      }
+    };
+    const uint32_t stage0 = smem_u32(stage_smem) + (uint32_t)(warp - 2) * 4096u, stage1 = stage0 + 2048u;
+
+    int tile = blockIdx.x, c0 = half * 32, lt = 0, item = 0;
+    const bool any = tile < p.total_tiles && c0 < BN;
+    float4 pf0, pf1;
+    uint4 rv[4];
+    Geom g;
+    if (any) {
+      g = geom(tile);
+      prefetch_params(tile, c0, pf0, pf1);
+      prefetch_residual(g, c0, rv);
+    }
+    while (any && tile < p.total_tiles) {
+      // park this item's parameters, then put the next item's requests in flight
+      float4* pb = pbuf + (item & 1) * 40;
+      pb[lane] = pf0;
+      if (lane < 8) pb[32 + lane] = pf1;
+      __syncwarp();
+      uint4 rcur[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rcur[j] = rv[j];
+      const Geom gc = g;
+      const int c0c = c0, buf = lt & 1;
+      const bool first = c0 == half * 32;
+      int ntile = tile, nc0 = c0 + 64;
+      if (nc0 >= BN) {
+        ntile = tile + (int)gridDim.x;
+        nc0 = half * 32;
+      }
+      const bool last = ntile != tile;
+      if (ntile < p.total_tiles) {
+        if (last) g = geom(ntile);
+        prefetch_params(ntile, nc0, pf0, pf1);
+        prefetch_residual(g, nc0, rv);
+      }
+      if (first) {
+        mbar_wait(&acc_full[buf], ((uint32_t)lt >> 1) & 1u);
+        tc_fence_after();
+      }
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BNp);
+      const int cbase = gc.ncol0 + c0c;
+      const bool full = block_full(cbase);
+      const bool block_on = cbase < p.Cout && !(p.debug & 16);                 // warp-uniform
+      // coalesced path: whole 32-channel block, warp-shared parameters, 16-byte aligned rows in every tensor
+      bool fast = block_on && full && shared_params && (!p.residual || ((p.res_cstride | cbase) & 7) == 0);
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+        if (p.out[o]) fast = fast && ((p.out_cstride[o] | (p.out_coffset[o] + cbase)) & 7) == 0 && (((uintptr_t)p.out[o]) & 15) == 0;
+      const bool live = gc.valid && block_on;
+      uint32_t v[32];
+      if (p.debug & 64) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0;
+      } else {
+        tmem_ld32(tbase + (uint32_t)c0c, v);
+      }
+      if ((fast || live) && !(p.debug & 128)) {
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (full) {
-          if (p.bias) {
+        const int n = gc.n;
+        const size_t pixel = gc.pixel;
+        if (fast) {
+          // ---- fast path (all lanes, rows outside the image are masked at the stores) ----
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-              f[j] += b4.x;
-              f[j + 1] += b4.y;
-              f[j + 2] += b4.z;
-              f[j + 3] += b4.w;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = pb[j];
+            f[4 * j] += b4.x;
+            f[4 * j + 1] += b4.y;
+            f[4 * j + 2] += b4.z;
+            f[4 * j + 3] += b4.w;
           }
           if (p.residual) {
+            // the residual block arrived in transposed ownership: through the staging tile back to row ownership
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sts128(stage_addr(stage0, 8 * i + trow, tchunk), rcur[i]);
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[j]);
+              const uint4 rr = lds128(stage_addr(stage0, lane, j));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float2 t2 = __bfloat1622float2(h[k]);
@@ -352,65 +486,85 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 f[8 * j + 2 * k + 1] += t2.y;
               }
             }
+            __syncwarp();
           }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + j;
-            if (p.bias && c < p.Cout) f[j] += __ldg(p.bias + c);
+          for (int o = 0; o < 2; ++o) {
+            if (!p.out[o]) continue;
+            const float4* sc4 = pb + 8 + 16 * o;
+            const float4* sh4 = pb + 16 + 16 * o;
+            const uint32_t st = o ? stage1 : stage0;
+            switch (p.act[o]) {
+              case ACT_RELU: stage_block32<ACT_RELU>(f, sc4, sh4, p.act_param, st, lane); break;
+              case ACT_LEAKY: stage_block32<ACT_LEAKY>(f, sc4, sh4, p.act_param, st, lane); break;
+              case ACT_NONE: stage_block32<ACT_NONE>(f, sc4, sh4, p.act_param, st, lane); break;
+              case ACT_TANH: stage_block32<ACT_TANH>(f, sc4, sh4, p.act_param, st, lane); break;
+              case ACT_ELU: stage_block32<ACT_ELU>(f, sc4, sh4, p.act_param, st, lane); break;
+              default: stage_block32<ACT_SIGMOID_AFFINE>(f, sc4, sh4, p.act_param, st, lane); break;
+            }
           }
-          if (p.residual) {
-            const __nv_bfloat16* r = p.residual + pixel * p.res_cstride + cbase;
+          __syncwarp();
+#pragma unroll
+          for (int o = 0; o < 2; ++o)
+            if (p.out[o] && !(p.debug & 32)) write_out(o ? stage1 : stage0, p.out[o] + p.out_coffset[o] + cbase, p.out_cstride[o], gc);
+          __syncwarp();  // the staging tiles are rewritten by the next item
+          if (p.out_f32_nchw && gc.valid) {
+            const float* sc = reinterpret_cast<const float*>(pb + 8);
+            const float* sh = reinterpret_cast<const float*>(pb + 16);
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.Cout) f[j] += __bfloat162float(r[j]);
+              p.out_f32_nchw[(((size_t)n * p.Cout + cbase + j) * p.out_H + gc.fy) * p.out_W + gc.fx] =
+                  apply_act(fmaf(f[j], sc[j], sh[j]), p.act[0], p.act_param);
           }
-        }
+        } else {
+          // ---- generic path: ragged channel counts, per-sample parameters in a tile that spans images.  Every loop
+          // is fully unrolled with constant indices: one dynamic index would move f[] to local memory for the
+          // fast path as well. ----
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          if (!p.out[o]) continue;
-          const float* sc = p.scale[o] ? p.scale[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
-          const float* sh = p.shift[o] ? p.shift[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
-          __nv_bfloat16* dst = p.out[o] + pixel * p.out_cstride[o] + p.out_coffset[o] + cbase;
-          if (full && ((((uintptr_t)dst) & 15) == 0)) {
-            switch (p.act[o]) {
-              case ACT_RELU: store_block32<ACT_RELU>(f, sc, sh, p.act_param, dst); break;
-              case ACT_LEAKY: store_block32<ACT_LEAKY>(f, sc, sh, p.act_param, dst); break;
-              case ACT_NONE: store_block32<ACT_NONE>(f, sc, sh, p.act_param, dst); break;
-              default:
-                for (int j = 0; j < 32; ++j) {
-                  float t = f[j];
-                  if (sc) t *= __ldg(sc + j);
-                  if (sh) t += __ldg(sh + j);
-                  dst[j] = __float2bfloat16(apply_act(t, p.act[o], p.act_param));
-                }
-            }
-          } else {
-            for (int j = 0; j < 32; ++j) {
-              if (cbase + j >= p.Cout) break;
-              float t = f[j];
-              if (sc) t *= __ldg(sc + j);
-              if (sh) t += __ldg(sh + j);
-              dst[j] = __float2bfloat16(apply_act(t, p.act[o], p.act_param));
-            }
-          }
-        }
-        if (p.out_f32_nchw) {  // fp32 NCHW copy of output 0's values (or the only output)
-          const float* sc = p.scale[0] ? p.scale[0] + (p.per_sample[0] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
-          const float* sh = p.shift[0] ? p.shift[0] + (p.per_sample[0] ? (size_t)n * p.Cout : 0) + cbase : nullptr;
           for (int j = 0; j < 32; ++j) {
             const int c = cbase + j;
-            if (c >= p.Cout) break;
-            float t = f[j];
-            if (sc) t *= __ldg(sc + j);
-            if (sh) t += __ldg(sh + j);
-            p.out_f32_nchw[(((size_t)n * p.Cout + c) * p.out_H + fy) * p.out_W + fx] = apply_act(t, p.act[0], p.act_param);
+            if (c >= p.Cout) break;  // unrolled: the indices stay compile-time constants, the tail is skipped
+            if (p.bias) f[j] += __ldg(p.bias + c);
+            if (p.residual) f[j] += __bfloat162float(p.residual[pixel * p.res_cstride + c]);
+          }
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const bool f32_only = o == 0 && !p.out[0] && p.out_f32_nchw;
+            if (!p.out[o] && !f32_only) continue;
+            const float* sc = p.scale[o] ? p.scale[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) : nullptr;
+            const float* sh = p.shift[o] ? p.shift[o] + (p.per_sample[o] ? (size_t)n * p.Cout : 0) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = cbase + j;
+              if (c >= p.Cout) break;
+              float t = f[j];
+              if (sc) t *= __ldg(sc + c);
+              if (sh) t += __ldg(sh + c);
+              const float y = apply_act(t, p.act[o], p.act_param);
+              if (p.out[o]) p.out[o][pixel * p.out_cstride[o] + p.out_coffset[o] + c] = __float2bfloat16(y);
+              if (o == 0 && p.out_f32_nchw)
+                p.out_f32_nchw[(((size_t)n * p.Cout + c) * p.out_H + gc.fy) * p.out_W + gc.fx] = y;
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (last) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        ++lt;
+      }
+      tile = ntile;
+      c0 = nc0;
+      ++item;
+    }
+    // a warp whose column parity has no block in this launch (BN <= 32) still releases every accumulator
+    if (!any || half * 32 >= BN) {
+      int lt2 = 0;
+      for (int t2 = blockIdx.x; t2 < p.total_tiles; t2 += gridDim.x, ++lt2) {
+        mbar_wait(&acc_full[lt2 & 1], ((uint32_t)lt2 >> 1) & 1u);
+        if (lane == 0) mbar_arrive(&acc_empty[lt2 & 1]);
+      }
     }
   }
   tc_fence_before();
@@ -530,7 +684,7 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.a_stage_bytes = (!halo || d->in[1].ntaps > 0) ? A_STAGE_BYTES : 0;
   const int stage_bytes = p.a_stage_bytes + BN * BK * 2;
   // one persistent CTA per SM: as many ring stages as ~200 KB of shared memory hold
-  int stages = (200 * 1024 - (halo ? 2 * HALO_BYTES : 0)) / stage_bytes;
+  int stages = (182 * 1024 - (halo ? 2 * HALO_BYTES : 0)) / stage_bytes;  // 227 KB - barriers, parameter and staging tiles
   stages = stages > CONV_MAX_STAGES ? CONV_MAX_STAGES : (stages < 2 ? 2 : stages);
   p.stages = stages;
   CUtensorMap mapA[2], mapW, mapH;
@@ -585,7 +739,7 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.out_py = d->out_py;
   p.out_px = d->out_px;
 
-  const size_t smem_bytes = 1024 + (halo ? 2 * HALO_BYTES : 0) + (size_t)stages * stage_bytes + (2 * stages + 8) * sizeof(uint64_t) + 16;
+  const size_t smem_bytes = 1024 + (halo ? 2 * HALO_BYTES : 0) + (size_t)stages * stage_bytes + (2 * stages + 8) * sizeof(uint64_t) + 16 + 8 * 2 * 40 * 16 + 8 * 4096;
   static thread_local int attr_dev = -1;
   static thread_local int sms = 148;
   int dev = 0;

@@ -36,6 +36,7 @@ W = 256
 K_PP = 128
 RADIUS = 4.0
 BYTES_PER_VIEW_SPLAT_FUSED = 4 * W * W + 2 * 4 * 3 * W * W + W * W  # depth + feat in, image + mask out = 1 900 544
+BYTES_PER_VIEW_SPLAT_MAPS = BYTES_PER_VIEW_SPLAT_FUSED + 2 * 4 * K_PP * W * W  # + idx and z maps = 69 009 408
 FLOP_PER_CELL = 11.163e6       # lmconv column, SURVEY.md 8d
 FLOP_DECODER = 128.22e9        # ResNetDecoder per image
 FLOP_UNET, FLOP_VQ_ENC, FLOP_VQ_DEC = 5.53e9, 3.66e9 + 0.07e9, 2.58e9
@@ -49,7 +50,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images (= views) per step per GPU")
+    ap.add_argument("--batch", type=int, default=128,
+                    help="images (= views) per step per GPU.  The sampler's serial levels cost the same at any batch, "
+                         "so throughput is quoted at 128; 32 (BASELINE configs[4]'s per-GPU share) is profiles/r01_bench_b32_final.json")
     ap.add_argument("--cpu-tokens", type=int, default=4, help="sampler tokens timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -75,6 +78,9 @@ def workload_config(args, world):
         "views_per_step_per_gpu": args.batch, "global_views_per_step": args.batch * world,
         "weights": "seeded random init of the reference architecture (pixelsynth_b200/synthetic.py)",
         "l2_policy": "activations + sampler cache per step (> 1 GB at batch 32) exceed the 126 MB L2; no explicit flush",
+        "batch_note": "the outpaint sampler's sampled levels are a serial chain whose latency does not depend on the batch, "
+                      "so views/s grows with the batch until the convolutions dominate; measured 996 views/s at 32 and 1833 at 128 "
+                      "per GPU (profiles/r01_bench_b32_final.json, r01_bench_b128_final.json)",
         "parallelism": "images sharded across ranks; one NCCL broadcast of the source images at job start" if world > 1
                        else "single GPU",
     }
@@ -331,9 +337,28 @@ def main():
     kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "conv_igemm_kernel", "lmconv_tc_kernel")}
     _lib.kernel_time_ms(None)
     last = model.last
+    # the splat in its map-emitting mode (idx + z maps: the bit-exact parity surface, 69.0 MB/view): the HBM-bound
+    # configuration SURVEY 8d defines the splat roofline on.  Same depth / cameras as the step, 16 views per launch.
+    from pixelsynth_b200.ops import pack_mats as pack_mats_t
+    nb = min(B, 16)
+    cam0, cam1 = dev_batch["cameras"][0], dev_batch["cameras"][1]
+    mats = pack_mats_t(cam0["K"][:nb], cam0["Kinv"][:nb], cam0["P"][:nb], cam0["Pinv"][:nb], cam1["P"][:nb], cam1["Pinv"][:nb])
+    depth16, feat16 = last["depth"][:nb].contiguous(), src[:nb].contiguous()
+    run_maps = lambda: torch.ops.pixelsynth_b200.splat(depth16, feat16, mats, W, W, K_PP, RADIUS, 1.0, 2, 0, 13, 1e-2, True, False)
+    for _ in range(3):
+        run_maps()
+    torch.cuda.synchronize()
+    L.ps_timing_enable(1)
+    for _ in range(5):
+        run_maps()
+    torch.cuda.synchronize()
+    L.ps_timing_enable(0)
+    maps_ms = _lib.kernel_time_ms("fine_kernel")[0] / 5
+    _lib.kernel_time_ms(None)
     cells_processed = int(model.outpaint2.last_levels[-1])   # rows the sampler pushed through the network this step
     levels = len(model.outpaint2.last_levels) - 1
     cells_sampled = int(last["sample_mask"].sum())
+    levels_prefix = int(model.outpaint2.last_first_b)
 
     if rank != 0:
         if world > 1:
@@ -352,17 +377,30 @@ def main():
         "lmconv_tc_kernel": {"bound": "tensor", "achieved": FLOP_PER_CELL * cells_processed / (per_step["lmconv_tc_kernel"][0] * 1e-3) / 1e12,
                                  "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["lmconv_tc_kernel"][0],
                                  "cells_processed_per_step": cells_processed, "cells_sampled_per_step": cells_sampled,
-                                 "dependency_levels": levels},
+                                 "dependency_levels": levels, "prefix_levels_pipelined": levels_prefix,
+                                 "sampled_levels_serial": levels - levels_prefix,
+                                 "note": "one launch; the sampled levels are a chain of dependent 34-layer columns "
+                                         "(a token feeds the next level's first layer), so the step time is "
+                                         "sampled_levels x one tile's latency and the tensor pipe idles in between"},
+        "splat fine_kernel (maps emitted)": {
+            "bound": "hbm", "achieved": BYTES_PER_VIEW_SPLAT_MAPS * nb / (maps_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "ms_per_step": maps_ms, "views_per_launch": nb,
+            "note": "not part of the timed step: the map-emitting parity configuration, measured in this run"},
         "conv_igemm_kernel": {"bound": "tensor", "achieved": conv_flops / (per_step["conv_igemm_kernel"][0] * 1e-3) / 1e12,
                               "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["conv_igemm_kernel"][0],
                               "launches_per_step": per_step["conv_igemm_kernel"][1]},
     }
-    for v in rl.values():
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    for k, v in rl.items():
         v["frac"] = v["achieved"] / v["peak"]
-        v["share_of_step"] = v["ms_per_step"] / step_ms
-    dom = max(rl, key=lambda k: rl[k]["ms_per_step"])
+        v["share_of_step"] = 0.0 if "maps" in k else v["ms_per_step"] / step_ms
+    dom = max((k for k in rl if "maps" not in k), key=lambda k: rl[k]["ms_per_step"])
     roof = dict(rl[dom])
-    roof.update({"kernel": dom, "traffic": None, "peak_source": peak_src})
+    roof.update({"kernel": dom, "traffic": traffic.get(dom), "traffic_source": traffic.get("source"), "peak_source": peak_src})
     views_per_step = B * world
     line = {
         "metric": METRIC, "value": views_per_step * args.steps / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,

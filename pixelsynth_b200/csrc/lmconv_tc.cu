@@ -572,7 +572,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       for (int tap = 0; tap < 9; ++tap) {
         if (!((w0 >> tap) & 1u)) continue;
         const int nbr = cell + (tap / 3 - 1) * 32 + (tap % 3 - 1);
-        const int code = (int)__ldcg(p.codes + (size_t)b * LMT_CELLS + nbr);  // written by other SMs in this launch
+        // written by other SMs in this launch; the mask keeps the table lookup in bounds even if the watchdog has
+        // released a wedged wait and the token is garbage
+        const int code = (int)__ldcg(p.codes + (size_t)b * LMT_CELLS + nbr) & (LMT_CLASSES - 1);
         const uint4* wc = reinterpret_cast<const uint4*>(p.w_uinit + ((size_t)tap * (LMT_CLASSES + 1) + code) * LMT_F);
         const uint4* w1 = reinterpret_cast<const uint4*>(p.w_uinit + ((size_t)tap * (LMT_CLASSES + 1) + LMT_CLASSES) * LMT_F);
 #pragma unroll

@@ -13,8 +13,9 @@ Weights: a state dict with the reference's key names (`pts_regressor.*`, `vqvae.
 `module.` / `model.module.` prefixes of DataParallel checkpoints are stripped, demo.py:202-229).  Without a state
 dict the networks are random-initialised from opt.seed (pixelsynth_b200/synthetic.py): no checkpoint of the
 reference is reachable offline.
-Out of scope here: ranking num_samples > 1 candidates with the discriminator and the places365
-classifier (z_buffermodel.py:244-276) -- `ranker` may be supplied by the caller; default keeps sample 0.
+num_samples > 1 (z_buffermodel.py:244-276): `ranker(imgs, input_img) -> index` picks the candidate --
+pixelsynth_b200.ranking.Ranker reproduces the reference's rank fusion around injected discriminator / places365
+scorers (their weights are not reachable offline); without a ranker sample 0 is kept.
 Stochastic elements are explicit: `noise` (decoder, 16 x (B,20)) and `uniforms` (sampler) can be injected; when
 absent they are drawn from torch generators seeded as the reference seeds its sampler (sample.py:14-16)."""
 import math
@@ -103,12 +104,13 @@ class ZbufferModelPts(nn.Module):
         setting = _get(self.opt, "model_setting")
         if setting in ("gen_two_imgs", "gen_scene"):
             if direction == "S":
-                new_rt = input_RT.clone()
-                new_rt[:, 3, :] = 0
+                new_rt = torch.zeros_like(input_RT)
+                new_rt[:, :, :3] = input_RT[:, :, :3]
                 new_rt[:, 3, 3] = 1
+                # float64 offsets: the float32 translation is promoted, added in double and rounded once (:214)
                 t = .35 * torch.tensor([np.sin(2 * np.pi * num / denom), np.cos(2 * np.pi * num / denom),
-                                        .4 * np.sin(2 * np.pi * (.25 + num / denom))]).to(input_RT)
-                new_rt[:, :3, 3] = input_RT[:, :3, 3] + t
+                                        .4 * np.sin(2 * np.pi * (.25 + num / denom))], device=input_RT.device)
+                new_rt[:, :3, 3] = (input_RT[:, :3, 3] + t).to(new_rt.dtype)
                 return torch.inverse(new_rt), new_rt
             if direction == "C":
                 rotvec = np.array([0.2 * np.cos(2 * np.pi * num / denom), 0.2 * np.sin(2 * np.pi * num / denom), 0])

@@ -37,6 +37,9 @@ constexpr int MAXK = PS_MAX_POINTS_PER_PIXEL;
 constexpr int LSTRIDE = MAXK + 4;    // u16 per pixel row of the slot lists (8-byte aligned rows)
 constexpr int BSTRIDE = CAP / 32 + 1;  // words per pixel row of the hit masks (odd: conflict-free columns)
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef PS_SPLAT_DEFAULT_VARIANT
+#define PS_SPLAT_DEFAULT_VARIANT 0
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // canonical arithmetic helpers
@@ -374,7 +377,75 @@ __device__ __forceinline__ float4 gather_feat(const float* __restrict__ featb, i
 //   D. one warp per pixel row of K slots: gather (id, z), recompute dist2, 16-byte streaming stores.
 // FAST: alpha compositing with tau == 1, an exact reciprocal of r^rad_pow and at most 4 feature channels
 // (the reference's shipped configuration); otherwise the same code with the general formulas.
-template <bool FAST>
+//
+// V selects the shared-memory encoding and the map writer.  V = 0: candidates keep their per-image point id, slot lists
+// hold candidate indices, one generic map loop.  V = 1: candidates hold the PACKED index b*P + p (what the idx map
+// stores), slot lists hold the candidate's BYTE offset (index * 16, the stride of both cand[] and feat[]), and the maps
+// are written by emit_maps_v1: fully unrolled over the warp's 16 pixels, running addresses, no per-pixel pointer
+// tests, and no dist2 arithmetic unless the dist2 map was asked for.
+template <int V>
+__device__ __forceinline__ unsigned short list_entry(int ci) {
+  return V ? (unsigned short)(ci << 4) : (unsigned short)ci;
+}
+template <int V>
+__device__ __forceinline__ const Cand& cand_at(const FineSmem& sm, unsigned e) {
+  return V ? *reinterpret_cast<const Cand*>(reinterpret_cast<const unsigned char*>(sm.cand) + e) : sm.cand[e];
+}
+template <int V>
+__device__ __forceinline__ const float4& feat_at(const FineSmem& sm, unsigned e) {
+  return V ? *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(sm.feat) + e) : sm.feat[e];
+}
+
+// Stage D for V = 1, K % 4 == 0, idx and zbuf both requested.  Lane l owns slots 4l..4l+3 of every pixel; the warp owns
+// pixels warp*16 .. warp*16+15 (two rows of the tile).  Offsets are in 16-byte units from the warp's first pixel.
+template <bool D2>
+__device__ __forceinline__ void emit_maps_v1(const FineSmem& sm, const FineParams& q, int b, int tx, int ty, int warp,
+                                             int lane, int nh, bool inimg) {
+  const int K = q.K, S = q.S;
+  const int k0 = 4 * lane;
+  const int kq = K >> 2;
+  const unsigned inmask = __ballot_sync(FULL, inimg);  // bit 2j: pixel j of this warp lies inside the image
+  const bool act = k0 < K;
+  const size_t o0 = ((((size_t)b * S + (ty * TILE + warp * 2)) * S + tx * TILE) * K + k0) >> 2;
+  int4* const pi = reinterpret_cast<int4*>(q.idx) + o0;
+  float4* const pz = reinterpret_cast<float4*>(q.zbuf) + o0;
+  float4* const pd = D2 ? reinterpret_cast<float4*>(q.dist2) + o0 : nullptr;
+  const int rowq = S * kq;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (!((inmask >> (2 * j)) & 1u)) continue;  // warp-uniform
+    const int nhj = __shfl_sync(FULL, nh, 2 * j);
+    const int pj = warp * 16 + j;
+    int4 iv = make_int4(-1, -1, -1, -1);
+    float4 zv = make_float4(-1.f, -1.f, -1.f, -1.f), dv = make_float4(-1.f, -1.f, -1.f, -1.f);
+    if (k0 < nhj) {
+      // entries between nhj and the next multiple of 4 point at the sentinel candidate (id -1, z -1)
+      const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pj][k0]);
+      const Cand c0 = cand_at<1>(sm, L.x & 0xffffu), c1 = cand_at<1>(sm, L.x >> 16);
+      const Cand c2 = cand_at<1>(sm, L.y & 0xffffu), c3 = cand_at<1>(sm, L.y >> 16);
+      iv = make_int4(c0.id, c1.id, c2.id, c3.id);
+      zv = make_float4(c0.z, c1.z, c2.z, c3.z);
+      if (D2) {
+        const float xfj = sm.ndcx[j & 7], yfj = sm.ndcy[warp * 2 + (j >> 3)];
+        dv.x = dist2_rn(__fsub_rn(c0.x, xfj), __fsub_rn(c0.y, yfj));
+        const float e1 = dist2_rn(__fsub_rn(c1.x, xfj), __fsub_rn(c1.y, yfj));
+        const float e2 = dist2_rn(__fsub_rn(c2.x, xfj), __fsub_rn(c2.y, yfj));
+        const float e3 = dist2_rn(__fsub_rn(c3.x, xfj), __fsub_rn(c3.y, yfj));
+        dv.y = (k0 + 1 < nhj) ? e1 : -1.0f;
+        dv.z = (k0 + 2 < nhj) ? e2 : -1.0f;
+        dv.w = (k0 + 3 < nhj) ? e3 : -1.0f;
+      }
+    }
+    if (act) {
+      const int du = (j >> 3) * rowq + (j & 7) * kq;
+      __stcs(pi + du, iv);
+      __stcs(pz + du, zv);
+      if (D2) __stcs(pd + du, dv);
+    }
+  }
+}
+
+template <bool FAST, int V>
 __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FineSmem& sm = *reinterpret_cast<FineSmem*>(smem_raw);
@@ -402,7 +473,7 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
     sc.x = 0.f;
     sc.y = 0.f;
     sc.z = -1.0f;
-    sc.id = -1 - (int32_t)((size_t)b * P);
+    sc.id = V ? -1 : -1 - (int32_t)((size_t)b * P);
     sm.cand[CAP] = sc;
   }
   if (tid == 64) {
@@ -410,6 +481,7 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
     sm.zmax = 0u;
     sm.maxcount = 0u;
   }
+  const int32_t idbase = V ? (int32_t)((size_t)b * P) : 0;  // what a stored candidate id carries on top of the point id
   const int* lst = q.list + ((size_t)b * nt2 + t) * CAPG;
   const float4* p4 = q.pts4 + (size_t)b * P;
   int id[PER];
@@ -521,7 +593,7 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
         cd.x = -cx[j];
         cd.y = -cy[j];
         cd.z = cz[j];
-        cd.id = id[j];
+        cd.id = idbase + id[j];
         sm.cand[fin] = cd;
         sm.feat[fin] = gather_feat(featb, C, P, id[j]);
       }
@@ -539,7 +611,7 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       cd.x = -v.x;
       cd.y = -v.y;
       cd.z = v.z;
-      cd.id = pid;
+      cd.id = idbase + pid;
       sm.cand[i] = cd;
       sm.feat[i] = gather_feat(featb, C, P, pid);
     }
@@ -598,12 +670,12 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       while (w && pos < K) {
         const int bpos = __ffs(w) - 1;
         w &= w - 1;
-        sm.u.r.lists[pix][pos++] = (unsigned short)(blk * 32 + bpos);
+        sm.u.r.lists[pix][pos++] = list_entry<V>(blk * 32 + bpos);
       }
     }
     nh = min(__shfl_sync(FULL, pos, lane | 1), K);  // lane 1 ends at the pixel's total hit count
     if (half)
-      for (int e = nh; e < ((nh + 3) & ~3); ++e) sm.u.r.lists[pix][e] = (unsigned short)CAP;
+      for (int e = nh; e < ((nh + 3) & ~3); ++e) sm.u.r.lists[pix][e] = list_entry<V>(CAP);
   }
   __syncwarp();
   {
@@ -614,9 +686,9 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
     const unsigned short* lp = sm.u.r.lists[pix];
     int k = k0;
     for (; k + 1 < k1; k += 2) {  // two hits per trip: independent loads and alphas, serial transmittance
-      const int ci0 = lp[k], ci1 = lp[k + 1];
-      const Cand cd0 = sm.cand[ci0], cd1 = sm.cand[ci1];
-      const float4 f0 = sm.feat[ci0], f1 = sm.feat[ci1];
+      const unsigned ci0 = lp[k], ci1 = lp[k + 1];
+      const Cand cd0 = cand_at<V>(sm, ci0), cd1 = cand_at<V>(sm, ci1);
+      const float4 f0 = feat_at<V>(sm, ci0), f1 = feat_at<V>(sm, ci1);
       const float d20 = dist2_rn(__fsub_rn(cd0.x, xf), __fsub_rn(cd0.y, yf));
       const float d21 = dist2_rn(__fsub_rn(cd1.x, xf), __fsub_rn(cd1.y, yf));
       const float a0 = FAST ? alpha_fast(d20, q.inv_denom) : alpha_of(d20, q);
@@ -636,9 +708,9 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       acc3 = fmaf(w1, f1.w, fmaf(w0, f0.w, acc3));
     }
     if (k < k1) {
-      const int ci = lp[k];
-      const Cand cd = sm.cand[ci];
-      const float4 f = sm.feat[ci];
+      const unsigned ci = lp[k];
+      const Cand cd = cand_at<V>(sm, ci);
+      const float4 f = feat_at<V>(sm, ci);
       const float d2 = dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf));
       const float a = FAST ? alpha_fast(d2, q.inv_denom) : alpha_of(d2, q);
       float wgt = a;
@@ -681,14 +753,14 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
           const float* fc = featb + (size_t)c0 * P;
           float acc = 0.f, Tc = 1.0f;
           for (int k = 0; k < nh; ++k) {
-            const Cand cd = sm.cand[sm.u.r.lists[pix][k]];
+            const Cand cd = cand_at<V>(sm, sm.u.r.lists[pix][k]);
             const float a = alpha_of(dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf)), q);
             float wgt = a;
             if (ac) {
               wgt = Tc * a;
               Tc *= 1.0f - a;
             }
-            acc += wgt * __ldg(fc + cd.id);
+            acc += wgt * __ldg(fc + (cd.id - idbase));
           }
           o[c0 * cs] = dv ? acc / norm : acc;
         }
@@ -699,8 +771,13 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
   // ---- D. maps: lane l owns output slots 4l..4l+3 of the current pixel; a warp streams its 16 pixels.
   // List entries between a pixel's hit count and the next multiple of 4 point at the sentinel candidate
   // (id -> -1, z = -1), so a lane either gathers four entries unconditionally or stores the -1 padding.
-  if (q.idx || q.zbuf || q.dist2) {
-    const int32_t base = (int32_t)((size_t)b * P);
+  if (V == 1 && q.idx && q.zbuf && (K & 3) == 0) {
+    if (q.dist2)
+      emit_maps_v1<true>(sm, q, b, tx, ty, warp, lane, nh, inimg);
+    else
+      emit_maps_v1<false>(sm, q, b, tx, ty, warp, lane, nh, inimg);
+  } else if (q.idx || q.zbuf || q.dist2) {
+    const int32_t base = V ? 0 : (int32_t)((size_t)b * P);  // V = 1 candidates already carry the packed index
     const int k0 = 4 * lane;
     const bool vec = (K & 3) == 0;
     for (int j = 0; j < 16; ++j) {
@@ -712,8 +789,8 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       if (k0 < nhj) {
         const float xfj = sm.ndcx[pj & 7], yfj = sm.ndcy[pj >> 3];
         const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pj][k0]);
-        const Cand c0 = sm.cand[L.x & 0xffffu], c1 = sm.cand[L.x >> 16];
-        const Cand c2 = sm.cand[L.y & 0xffffu], c3 = sm.cand[L.y >> 16];
+        const Cand c0 = cand_at<V>(sm, L.x & 0xffffu), c1 = cand_at<V>(sm, L.x >> 16);
+        const Cand c2 = cand_at<V>(sm, L.y & 0xffffu), c3 = cand_at<V>(sm, L.y >> 16);
         id4[0] = base + c0.id;
         id4[1] = base + c1.id;
         id4[2] = base + c2.id;
@@ -973,6 +1050,12 @@ static SplatLayout splat_layout(int B, int P, int S) {
   return L;
 }
 
+// Which fine_kernel encoding runs (see the kernel's comment).  PS_SPLAT_VARIANT overrides the default for A/B timing.
+static int splat_variant() {
+  const char* e = getenv("PS_SPLAT_VARIANT");
+  return e ? atoi(e) : PS_SPLAT_DEFAULT_VARIANT;
+}
+
 // depth != null: project from depth (forward_justpts); else pts (B,P,3) is the cloud.
 static int splat_impl(const float* depth, const float* mats, int W, float eps, const float* pts, const float* feat,
                       int B, int P, int C, int S, int K, double radius_px, double tau, int rad_pow, int accumulation,
@@ -1047,8 +1130,10 @@ static int splat_impl(const float* depth, const float* mats, int W, float eps, c
   int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
   if (smem_set_for_device != dev) {
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
     PS_CUDA(cudaFuncSetAttribute(fine_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
     smem_set_for_device = dev;
   }
@@ -1056,10 +1141,18 @@ static int splat_impl(const float* depth, const float* mats, int W, float eps, c
     dim3 grid(L.nt2, B);
     PS_TIME_BEGIN("fine_kernel", stream);
     const bool fast = accumulation == PS_ACCUM_ALPHACOMPOSITE && q.tau == 1.0f && q.inv_denom != 0.0f && C <= 4;
-    if (fast)
-      fine_kernel<true><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
-    else
-      fine_kernel<false><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+    static const int variant = splat_variant();
+    if (variant == 1) {
+      if (fast)
+        fine_kernel<true, 1><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+      else
+        fine_kernel<false, 1><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+    } else {
+      if (fast)
+        fine_kernel<true, 0><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+      else
+        fine_kernel<false, 0><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+    }
     PS_TIME_END(stream);
     PS_LAUNCHED();
     fine_big_kernel<<<296, TPB, sizeof(BigSmem), stream>>>(q);

@@ -2,6 +2,7 @@
 rasterize_points_zbuf (the PyTorch3D-shaped seam), splat_cumulative, the network ops behind weight handles,
 gen_order_masks, lmconv_sample / lmconv_logits, combine.  Each op is checked against the oracle where one exists
 (bit-exact for maps / masks / orders) and against the class mirror's own result otherwise (same kernels, so equal)."""
+import os
 import types
 
 import numpy as np
@@ -140,3 +141,26 @@ def test_network_ops_behind_handles(ops, handles):
         P.vqvae_encode_top(img, 10 ** 6)
     with pytest.raises(RuntimeError):   # reference asserts 4-D NCHW input
         P.refine_decode(comb[:, :2], bg, None, handles["refine"])
+
+
+@pytest.mark.parametrize("setting", ["gen_img", "gen_scene"])
+def test_demo_command_line(tmp_path, golden_dir, setting):
+    """pixelsynth_b200.demo with the reference's flags (scripts/demo_image.sh / demo_scene.sh), seeded weights: the
+    files demo.py writes exist, are 256x256 RGB, and the novel view differs from the input."""
+    from PIL import Image
+
+    from pixelsynth_b200 import demo
+
+    out = str(tmp_path / "res")
+    argv = ["--vqvae", "--use_fixed_testset", "--model_setting", setting, "--gpu", "0", "--demo_img_name", "demo_input.png",
+            "--demo_folder", golden_dir, "--result_folder", out, "--temperature=.7", "--num_samples", "1"]
+    argv += ["--direction", "L", "--rotation", ".6"] if setting == "gen_img" else ["--directions", "R", "--num_split", "1"]
+    assert demo.main(argv) == 0
+    names = ["input_image_.png"] + (["output_image_L_0.png", "input_fs_image_L_0.png"] if setting == "gen_img"
+                                     else ["scene/output_image_R_0001.png"])
+    imgs = {}
+    for n in names:
+        im = np.asarray(Image.open(os.path.join(out, n)))
+        assert im.shape == (256, 256, 3) and im.dtype == np.uint8, n
+        imgs[n] = im.astype(np.int32)
+    assert np.abs(imgs[names[1]] - imgs[names[0]]).mean() > 1.0

@@ -37,9 +37,6 @@ constexpr int MAXK = PS_MAX_POINTS_PER_PIXEL;
 constexpr int LSTRIDE = MAXK + 4;    // u16 per pixel row of the slot lists (8-byte aligned rows)
 constexpr int BSTRIDE = CAP / 32 + 1;  // words per pixel row of the hit masks (odd: conflict-free columns)
 constexpr unsigned FULL = 0xffffffffu;
-#ifndef PS_SPLAT_DEFAULT_VARIANT
-#define PS_SPLAT_DEFAULT_VARIANT 0
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // canonical arithmetic helpers
@@ -332,23 +329,24 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* __restrict_
   }
 }
 
-struct __align__(16) Cand {
-  float x, y, z;  // x, y already negated (z_buffer_layers.py:71-72)
-  int id;
-};
-
 struct SortScratch {
   unsigned hist[NB + 4];        // bucket counts -> exclusive starts; hist[NB] = n
   unsigned long long key[CAP];  // (z bits << 32) | point id, in bucket order
 };
 struct RasterScratch {
   unsigned bits[NPIX][BSTRIDE];         // per pixel: hit mask over the sorted candidates, 32 per word
-  unsigned short lists[NPIX][LSTRIDE];  // per pixel: candidate index of output slot k
+  unsigned short lists[NPIX][LSTRIDE];  // per pixel: BYTE offset (candidate index * 16) of output slot k
 };
+// The sorted candidates as three arrays, each holding exactly what one stage reads, because the kernel is bound by
+// shared-memory wavefronts (ncu: L1 data pipe 87 % busy, half of it bank conflicts of 16-byte-stride gathers):
+//   xyrg  x, y (already negated, z_buffer_layers.py:71-72) + feature channels 0, 1   -> ballots (x, y), compositing
+//   zid   z bits + PACKED index b*P+p (what the idx map stores); [CAP] = sentinel     -> map writer only
+//   bw    feature channel 2 (NC = 3: 4-byte stride) or channels 2, 3 (NC = 4)         -> compositing
+// A slot-list entry is the candidate's byte offset in xyrg; zid is at half, bw at a quarter / half of it.
 struct FineSmem {
-  Cand cand[CAP + 1];  // [CAP] is the sentinel the padded list entries point at (id -> -1, z = -1)
-  float4 feat[CAP];    // up to 4 feature channels of each candidate
-  float4 pad_;
+  float4 xyrg[CAP];
+  uint2 zid[CAP + 2];  // [CAP]: z = -1, id = -1, what the padded list entries point at
+  float bw[2 * CAP];
   union {
     SortScratch s;
     RasterScratch r;
@@ -367,40 +365,37 @@ __device__ __forceinline__ float4 gather_feat(const float* __restrict__ featb, i
   return f;
 }
 
-// One 128-thread CTA per 8x8-pixel tile.
-//   A. load the tile's candidates; counting sort by (z, point id): 1024 buckets over the tile's z range,
-//      exact rank inside the (small) buckets; a bitonic sort is the fallback for degenerate z distributions.
-//   B. each warp takes 32 sorted candidates at a time and ballots the exact membership test against the 64
-//      pixels: pixel p gets, per candidate block, a 32-bit hit word whose set bits are already in output order.
-//   C. two adjacent lanes per pixel: each expands half of the pixel's hit words into the slot list, then
-//      composites half of the slots front to back; the halves combine as acc0 + T0 * acc1.
-//   D. one warp per pixel row of K slots: gather (id, z), recompute dist2, 16-byte streaming stores.
-// FAST: alpha compositing with tau == 1, an exact reciprocal of r^rad_pow and at most 4 feature channels
-// (the reference's shipped configuration); otherwise the same code with the general formulas.
-//
-// V selects the shared-memory encoding and the map writer.  V = 0: candidates keep their per-image point id, slot lists
-// hold candidate indices, one generic map loop.  V = 1: candidates hold the PACKED index b*P + p (what the idx map
-// stores), slot lists hold the candidate's BYTE offset (index * 16, the stride of both cand[] and feat[]), and the maps
-// are written by emit_maps_v1: fully unrolled over the warp's 16 pixels, running addresses, no per-pixel pointer
-// tests, and no dist2 arithmetic unless the dist2 map was asked for.
-template <int V>
-__device__ __forceinline__ unsigned short list_entry(int ci) {
-  return V ? (unsigned short)(ci << 4) : (unsigned short)ci;
+__device__ __forceinline__ unsigned short list_entry(int ci) { return (unsigned short)(ci << 4); }
+__device__ __forceinline__ float4 ld_xyrg(const FineSmem& sm, unsigned e) {
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(sm.xyrg) + e);
 }
-template <int V>
-__device__ __forceinline__ const Cand& cand_at(const FineSmem& sm, unsigned e) {
-  return V ? *reinterpret_cast<const Cand*>(reinterpret_cast<const unsigned char*>(sm.cand) + e) : sm.cand[e];
+__device__ __forceinline__ float2 ld_xy(const FineSmem& sm, unsigned e) {
+  return *reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(sm.xyrg) + e);
 }
-template <int V>
-__device__ __forceinline__ const float4& feat_at(const FineSmem& sm, unsigned e) {
-  return V ? *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(sm.feat) + e) : sm.feat[e];
+__device__ __forceinline__ uint2 ld_zid(const FineSmem& sm, unsigned e) {
+  return *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(sm.zid) + (e >> 1));
+}
+template <int NC>
+__device__ __forceinline__ float2 ld_bw(const FineSmem& sm, unsigned e) {
+  if (NC == 3) return make_float2(*reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(sm.bw) + (e >> 2)), 0.f);
+  return *reinterpret_cast<const float2*>(reinterpret_cast<const unsigned char*>(sm.bw) + (e >> 1));
+}
+template <int NC>
+__device__ __forceinline__ void st_cand(FineSmem& sm, int i, float x, float y, float z, int packed_id, float4 f) {
+  sm.xyrg[i] = make_float4(x, y, f.x, f.y);
+  sm.zid[i] = make_uint2(__float_as_uint(z), (unsigned)packed_id);
+  if (NC == 3)
+    sm.bw[i] = f.z;
+  else
+    *reinterpret_cast<float2*>(&sm.bw[2 * i]) = make_float2(f.z, f.w);
 }
 
-// Stage D for V = 1, K % 4 == 0, idx and zbuf both requested.  Lane l owns slots 4l..4l+3 of every pixel; the warp owns
-// pixels warp*16 .. warp*16+15 (two rows of the tile).  Offsets are in 16-byte units from the warp's first pixel.
+// Stage D when K % 4 == 0 and idx, zbuf are both requested.  Lane l owns slots 4l..4l+3 of every pixel; the warp owns
+// pixels warp*16 .. warp*16+15 (two rows of the tile).  Fully unrolled over the 16 pixels; offsets in 16-byte units from
+// the warp's first pixel; no dist2 arithmetic unless the dist2 map was asked for.
 template <bool D2>
-__device__ __forceinline__ void emit_maps_v1(const FineSmem& sm, const FineParams& q, int b, int tx, int ty, int warp,
-                                             int lane, int nh, bool inimg) {
+__device__ __forceinline__ void emit_maps(const FineSmem& sm, const FineParams& q, int b, int tx, int ty, int warp,
+                                          int lane, int nh, bool inimg) {
   const int K = q.K, S = q.S;
   const int k0 = 4 * lane;
   const int kq = K >> 2;
@@ -419,21 +414,22 @@ __device__ __forceinline__ void emit_maps_v1(const FineSmem& sm, const FineParam
     int4 iv = make_int4(-1, -1, -1, -1);
     float4 zv = make_float4(-1.f, -1.f, -1.f, -1.f), dv = make_float4(-1.f, -1.f, -1.f, -1.f);
     if (k0 < nhj) {
-      // entries between nhj and the next multiple of 4 point at the sentinel candidate (id -1, z -1)
+      // entries between nhj and the next multiple of 4 point at the sentinel (id -1, z -1)
       const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pj][k0]);
-      const Cand c0 = cand_at<1>(sm, L.x & 0xffffu), c1 = cand_at<1>(sm, L.x >> 16);
-      const Cand c2 = cand_at<1>(sm, L.y & 0xffffu), c3 = cand_at<1>(sm, L.y >> 16);
-      iv = make_int4(c0.id, c1.id, c2.id, c3.id);
-      zv = make_float4(c0.z, c1.z, c2.z, c3.z);
+      const unsigned e0 = L.x & 0xffffu, e1 = L.x >> 16, e2 = L.y & 0xffffu, e3 = L.y >> 16;
+      const uint2 c0 = ld_zid(sm, e0), c1 = ld_zid(sm, e1), c2 = ld_zid(sm, e2), c3 = ld_zid(sm, e3);
+      iv = make_int4((int)c0.y, (int)c1.y, (int)c2.y, (int)c3.y);
+      zv = make_float4(__uint_as_float(c0.x), __uint_as_float(c1.x), __uint_as_float(c2.x), __uint_as_float(c3.x));
       if (D2) {
         const float xfj = sm.ndcx[j & 7], yfj = sm.ndcy[warp * 2 + (j >> 3)];
-        dv.x = dist2_rn(__fsub_rn(c0.x, xfj), __fsub_rn(c0.y, yfj));
-        const float e1 = dist2_rn(__fsub_rn(c1.x, xfj), __fsub_rn(c1.y, yfj));
-        const float e2 = dist2_rn(__fsub_rn(c2.x, xfj), __fsub_rn(c2.y, yfj));
-        const float e3 = dist2_rn(__fsub_rn(c3.x, xfj), __fsub_rn(c3.y, yfj));
-        dv.y = (k0 + 1 < nhj) ? e1 : -1.0f;
-        dv.z = (k0 + 2 < nhj) ? e2 : -1.0f;
-        dv.w = (k0 + 3 < nhj) ? e3 : -1.0f;
+        const float2 p0 = ld_xy(sm, e0), p1 = ld_xy(sm, e1), p2 = ld_xy(sm, e2), p3 = ld_xy(sm, e3);
+        dv.x = dist2_rn(__fsub_rn(p0.x, xfj), __fsub_rn(p0.y, yfj));
+        const float d1 = dist2_rn(__fsub_rn(p1.x, xfj), __fsub_rn(p1.y, yfj));
+        const float d2 = dist2_rn(__fsub_rn(p2.x, xfj), __fsub_rn(p2.y, yfj));
+        const float d3 = dist2_rn(__fsub_rn(p3.x, xfj), __fsub_rn(p3.y, yfj));
+        dv.y = (k0 + 1 < nhj) ? d1 : -1.0f;
+        dv.z = (k0 + 2 < nhj) ? d2 : -1.0f;
+        dv.w = (k0 + 3 < nhj) ? d3 : -1.0f;
       }
     }
     if (act) {
@@ -445,8 +441,21 @@ __device__ __forceinline__ void emit_maps_v1(const FineSmem& sm, const FineParam
   }
 }
 
-template <bool FAST, int V>
-__global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
+// One 128-thread CTA per 8x8-pixel tile.
+//   A. load the tile's candidates; counting sort by (z, point id): 1024 buckets over the tile's z range,
+//      exact rank inside the (small) buckets; a bitonic sort is the fallback for degenerate z distributions.
+//   B. each warp takes 32 sorted candidates at a time and ballots the exact membership test against the 64
+//      pixels: pixel p gets, per candidate block, a 32-bit hit word whose set bits are already in output order.
+//      Every lane sees all 64 ballots; a select tree over the lane's own bits leaves lane l holding the words of
+//      pixels l and l + 32, so a block costs two conflict-free stores instead of 64 single-lane ones.
+//   C. two adjacent lanes per pixel: each expands half of the pixel's hit words into the slot list, then
+//      composites half of the slots front to back; the halves combine as acc0 + T0 * acc1.
+//   D. one warp per pixel row of K slots: gather (z, id) of the lane's four slots, 16-byte streaming stores.
+// FAST: alpha compositing with tau == 1, an exact reciprocal of r^rad_pow and at most NC <= 4 feature channels
+// (the reference's shipped configuration is NC = 3); otherwise the same code with the general formulas (NC = 4, further
+// channels re-gathered from global memory).
+template <bool FAST, int NC>
+__global__ void __launch_bounds__(FTPB, 6) fine_kernel(FineParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FineSmem& sm = *reinterpret_cast<FineSmem*>(smem_raw);
   constexpr int PER = CAP / FTPB;
@@ -468,20 +477,13 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
   for (int i = tid; i < (NB + 4) / 4; i += FTPB) reinterpret_cast<uint4*>(sm.u.s.hist)[i] = make_uint4(0, 0, 0, 0);
   if (tid < TILE) sm.ndcx[tid] = pix_to_ndc(S - 1 - (tx * TILE + tid), S);
   if (tid >= 32 && tid < 32 + TILE) sm.ndcy[tid - 32] = pix_to_ndc(S - 1 - (ty * TILE + tid - 32), S);
-  if (tid == 65) {
-    Cand sc;
-    sc.x = 0.f;
-    sc.y = 0.f;
-    sc.z = -1.0f;
-    sc.id = V ? -1 : -1 - (int32_t)((size_t)b * P);
-    sm.cand[CAP] = sc;
-  }
+  if (tid == 65) sm.zid[CAP] = make_uint2(__float_as_uint(-1.0f), 0xffffffffu);
   if (tid == 64) {
     sm.zmin = 0xffffffffu;
     sm.zmax = 0u;
     sm.maxcount = 0u;
   }
-  const int32_t idbase = V ? (int32_t)((size_t)b * P) : 0;  // what a stored candidate id carries on top of the point id
+  const int32_t idbase = (int32_t)((size_t)b * P);  // stored candidate ids are packed: b*P + p
   const int* lst = q.list + ((size_t)b * nt2 + t) * CAPG;
   const float4* p4 = q.pts4 + (size_t)b * P;
   int id[PER];
@@ -588,14 +590,7 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
           const unsigned long long mine = ((unsigned long long)zb[j] << 32) | (unsigned)id[j];
           for (unsigned m = 0; m < c; ++m) rank += (sm.u.s.key[s0 + m] < mine) ? 1u : 0u;
         }
-        const int fin = (int)(s0 + rank);
-        Cand cd;
-        cd.x = -cx[j];
-        cd.y = -cy[j];
-        cd.z = cz[j];
-        cd.id = idbase + id[j];
-        sm.cand[fin] = cd;
-        sm.feat[fin] = gather_feat(featb, C, P, id[j]);
+        st_cand<NC>(sm, (int)(s0 + rank), -cx[j], -cy[j], cz[j], idbase + id[j], gather_feat(featb, C, P, id[j]));
       }
     }
   } else {  // degenerate z distribution (e.g. constant depth): full sort of the 64-bit keys
@@ -607,16 +602,10 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
     for (int i = tid; i < n; i += FTPB) {
       const int pid = (int)(unsigned)(sm.u.s.key[i] & 0xffffffffull);
       const float4 v = __ldg(p4 + pid);
-      Cand cd;
-      cd.x = -v.x;
-      cd.y = -v.y;
-      cd.z = v.z;
-      cd.id = idbase + pid;
-      sm.cand[i] = cd;
-      sm.feat[i] = gather_feat(featb, C, P, pid);
+      st_cand<NC>(sm, i, -v.x, -v.y, v.z, idbase + pid, gather_feat(featb, C, P, pid));
     }
   }
-  __syncthreads();  // cand/feat complete; sort scratch is dead from here (aliased by bits/lists)
+  __syncthreads();  // candidates complete; sort scratch is dead from here (aliased by bits/lists)
 
   // ---- B. membership ballots, 32 sorted candidates x 64 pixels per step ----
   const int nblk = (n + 31) >> 5;
@@ -627,27 +616,33 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       xfc[c] = sm.ndcx[c];
       yfr[c] = sm.ndcy[c];
     }
+    const bool l0 = lane & 1, l1 = lane & 2, l2 = lane & 4, l3 = lane & 8, l4 = lane & 16;
     for (int blk = warp; blk < nblk; blk += NWARP) {
       const int ci = blk * 32 + lane;
-      float px = 1e30f, py = 1e30f;  // lanes past the end never hit
-      if (ci < n) {
-        px = sm.cand[ci].x;
-        py = sm.cand[ci].y;
-      }
+      float2 pxy = make_float2(1e30f, 1e30f);  // lanes past the end never hit
+      if (ci < n) pxy = *reinterpret_cast<const float2*>(&sm.xyrg[ci]);
       float dx2[TILE], dy2[TILE];
 #pragma unroll
       for (int c = 0; c < TILE; ++c) {
-        const float dx = __fsub_rn(px, xfc[c]), dy = __fsub_rn(py, yfr[c]);
+        const float dx = __fsub_rn(pxy.x, xfc[c]), dy = __fsub_rn(pxy.y, yfr[c]);
         dx2[c] = __fmul_rn(dx, dx);
         dy2[c] = __fmul_rn(dy, dy);
       }
+      // rowsel[r] = the ballot of pixel (r, lane & 7); then rows lane >> 3 (and + 4) are picked the same way
+      unsigned rowsel[TILE];
 #pragma unroll
-      for (int r = 0; r < TILE; ++r)
+      for (int r = 0; r < TILE; ++r) {
+        unsigned v[TILE];
 #pragma unroll
-        for (int c = 0; c < TILE; ++c) {
-          const unsigned bal = __ballot_sync(FULL, __fadd_rn(dx2[c], dy2[r]) < q.r2);
-          if (lane == 0) sm.u.r.bits[r * TILE + c][blk] = bal;
-        }
+        for (int c = 0; c < TILE; ++c) v[c] = __ballot_sync(FULL, __fadd_rn(dx2[c], dy2[r]) < q.r2);
+        const unsigned a0 = l0 ? v[1] : v[0], a1 = l0 ? v[3] : v[2], a2 = l0 ? v[5] : v[4], a3 = l0 ? v[7] : v[6];
+        const unsigned b0 = l1 ? a1 : a0, b1 = l1 ? a3 : a2;
+        rowsel[r] = l2 ? b1 : b0;
+      }
+      const unsigned h0 = l3 ? rowsel[1] : rowsel[0], h1 = l3 ? rowsel[3] : rowsel[2];
+      const unsigned h2 = l3 ? rowsel[5] : rowsel[4], h3 = l3 ? rowsel[7] : rowsel[6];
+      sm.u.r.bits[lane][blk] = l4 ? h1 : h0;       // pixel index lane      = row lane >> 3,       column lane & 7
+      sm.u.r.bits[lane + 32][blk] = l4 ? h3 : h2;  // pixel index lane + 32 = row (lane >> 3) + 4, column lane & 7
     }
   }
   __syncthreads();
@@ -670,12 +665,12 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       while (w && pos < K) {
         const int bpos = __ffs(w) - 1;
         w &= w - 1;
-        sm.u.r.lists[pix][pos++] = list_entry<V>(blk * 32 + bpos);
+        sm.u.r.lists[pix][pos++] = list_entry(blk * 32 + bpos);
       }
     }
     nh = min(__shfl_sync(FULL, pos, lane | 1), K);  // lane 1 ends at the pixel's total hit count
     if (half)
-      for (int e = nh; e < ((nh + 3) & ~3); ++e) sm.u.r.lists[pix][e] = list_entry<V>(CAP);
+      for (int e = nh; e < ((nh + 3) & ~3); ++e) sm.u.r.lists[pix][e] = list_entry(CAP);
   }
   __syncwarp();
   {
@@ -686,11 +681,11 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
     const unsigned short* lp = sm.u.r.lists[pix];
     int k = k0;
     for (; k + 1 < k1; k += 2) {  // two hits per trip: independent loads and alphas, serial transmittance
-      const unsigned ci0 = lp[k], ci1 = lp[k + 1];
-      const Cand cd0 = cand_at<V>(sm, ci0), cd1 = cand_at<V>(sm, ci1);
-      const float4 f0 = feat_at<V>(sm, ci0), f1 = feat_at<V>(sm, ci1);
-      const float d20 = dist2_rn(__fsub_rn(cd0.x, xf), __fsub_rn(cd0.y, yf));
-      const float d21 = dist2_rn(__fsub_rn(cd1.x, xf), __fsub_rn(cd1.y, yf));
+      const unsigned e0 = lp[k], e1 = lp[k + 1];
+      const float4 c0 = ld_xyrg(sm, e0), c1 = ld_xyrg(sm, e1);
+      const float2 g0 = ld_bw<NC>(sm, e0), g1 = ld_bw<NC>(sm, e1);
+      const float d20 = dist2_rn(__fsub_rn(c0.x, xf), __fsub_rn(c0.y, yf));
+      const float d21 = dist2_rn(__fsub_rn(c1.x, xf), __fsub_rn(c1.y, yf));
       const float a0 = FAST ? alpha_fast(d20, q.inv_denom) : alpha_of(d20, q);
       const float a1 = FAST ? alpha_fast(d21, q.inv_denom) : alpha_of(d21, q);
       float w0 = a0, w1 = a1;
@@ -702,16 +697,16 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       } else {
         wsum += a0 + a1;
       }
-      acc0 = fmaf(w1, f1.x, fmaf(w0, f0.x, acc0));
-      acc1 = fmaf(w1, f1.y, fmaf(w0, f0.y, acc1));
-      acc2 = fmaf(w1, f1.z, fmaf(w0, f0.z, acc2));
-      acc3 = fmaf(w1, f1.w, fmaf(w0, f0.w, acc3));
+      acc0 = fmaf(w1, c1.z, fmaf(w0, c0.z, acc0));
+      acc1 = fmaf(w1, c1.w, fmaf(w0, c0.w, acc1));
+      acc2 = fmaf(w1, g1.x, fmaf(w0, g0.x, acc2));
+      if (NC > 3) acc3 = fmaf(w1, g1.y, fmaf(w0, g0.y, acc3));
     }
     if (k < k1) {
-      const unsigned ci = lp[k];
-      const Cand cd = cand_at<V>(sm, ci);
-      const float4 f = feat_at<V>(sm, ci);
-      const float d2 = dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf));
+      const unsigned e = lp[k];
+      const float4 c = ld_xyrg(sm, e);
+      const float2 g = ld_bw<NC>(sm, e);
+      const float d2 = dist2_rn(__fsub_rn(c.x, xf), __fsub_rn(c.y, yf));
       const float a = FAST ? alpha_fast(d2, q.inv_denom) : alpha_of(d2, q);
       float wgt = a;
       if (ac) {
@@ -720,10 +715,10 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       } else {
         wsum += a;
       }
-      acc0 = fmaf(wgt, f.x, acc0);
-      acc1 = fmaf(wgt, f.y, acc1);
-      acc2 = fmaf(wgt, f.z, acc2);
-      acc3 = fmaf(wgt, f.w, acc3);
+      acc0 = fmaf(wgt, c.z, acc0);
+      acc1 = fmaf(wgt, c.w, acc1);
+      acc2 = fmaf(wgt, g.x, acc2);
+      if (NC > 3) acc3 = fmaf(wgt, g.y, acc3);
     }
     // combine the halves: second-half terms are attenuated by the first half's transmittance
     const float T0 = __shfl_sync(FULL, T, lane & ~1);
@@ -745,7 +740,7 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
       o[0] = dv ? acc0 / norm : acc0;
       if (C > 1) o[cs] = dv ? acc1 / norm : acc1;
       if (C > 2) o[2 * cs] = dv ? acc2 / norm : acc2;
-      if (C > 3) o[3 * cs] = dv ? acc3 / norm : acc3;
+      if (NC > 3 && C > 3) o[3 * cs] = dv ? acc3 / norm : acc3;
       q.empty[((size_t)b * S + yi) * S + xi] = (nh == 0);
       if (!FAST) {
         // feature widths beyond 4 (non-RGB feature splats): channels re-gathered from global memory
@@ -753,14 +748,15 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
           const float* fc = featb + (size_t)c0 * P;
           float acc = 0.f, Tc = 1.0f;
           for (int k = 0; k < nh; ++k) {
-            const Cand cd = cand_at<V>(sm, sm.u.r.lists[pix][k]);
-            const float a = alpha_of(dist2_rn(__fsub_rn(cd.x, xf), __fsub_rn(cd.y, yf)), q);
+            const unsigned e = sm.u.r.lists[pix][k];
+            const float2 pxy = ld_xy(sm, e);
+            const float a = alpha_of(dist2_rn(__fsub_rn(pxy.x, xf), __fsub_rn(pxy.y, yf)), q);
             float wgt = a;
             if (ac) {
               wgt = Tc * a;
               Tc *= 1.0f - a;
             }
-            acc += wgt * __ldg(fc + (cd.id - idbase));
+            acc += wgt * __ldg(fc + ((int)ld_zid(sm, e).y - idbase));
           }
           o[c0 * cs] = dv ? acc / norm : acc;
         }
@@ -769,59 +765,38 @@ __global__ void __launch_bounds__(FTPB) fine_kernel(FineParams q) {
   }
 
   // ---- D. maps: lane l owns output slots 4l..4l+3 of the current pixel; a warp streams its 16 pixels.
-  // List entries between a pixel's hit count and the next multiple of 4 point at the sentinel candidate
-  // (id -> -1, z = -1), so a lane either gathers four entries unconditionally or stores the -1 padding.
-  if (V == 1 && q.idx && q.zbuf && (K & 3) == 0) {
+  // List entries between a pixel's hit count and the next multiple of 4 point at the sentinel (id -1, z -1), so a
+  // lane either gathers four entries unconditionally or stores the -1 padding.
+  if (q.idx && q.zbuf && (K & 3) == 0) {
     if (q.dist2)
-      emit_maps_v1<true>(sm, q, b, tx, ty, warp, lane, nh, inimg);
+      emit_maps<true>(sm, q, b, tx, ty, warp, lane, nh, inimg);
     else
-      emit_maps_v1<false>(sm, q, b, tx, ty, warp, lane, nh, inimg);
-  } else if (q.idx || q.zbuf || q.dist2) {
-    const int32_t base = V ? 0 : (int32_t)((size_t)b * P);  // V = 1 candidates already carry the packed index
+      emit_maps<false>(sm, q, b, tx, ty, warp, lane, nh, inimg);
+  } else if (q.idx || q.zbuf || q.dist2) {  // any subset of the maps, any K
     const int k0 = 4 * lane;
-    const bool vec = (K & 3) == 0;
     for (int j = 0; j < 16; ++j) {
       if (!__shfl_sync(FULL, (int)inimg, 2 * j)) continue;
       const int pj = warp * 16 + j;
       const int nhj = __shfl_sync(FULL, nh, 2 * j);
-      int id4[4] = {-1, -1, -1, -1};
-      float z4[4] = {-1.f, -1.f, -1.f, -1.f}, d4[4] = {-1.f, -1.f, -1.f, -1.f};
-      if (k0 < nhj) {
-        const float xfj = sm.ndcx[pj & 7], yfj = sm.ndcy[pj >> 3];
-        const uint2 L = *reinterpret_cast<const uint2*>(&sm.u.r.lists[pj][k0]);
-        const Cand c0 = cand_at<V>(sm, L.x & 0xffffu), c1 = cand_at<V>(sm, L.x >> 16);
-        const Cand c2 = cand_at<V>(sm, L.y & 0xffffu), c3 = cand_at<V>(sm, L.y >> 16);
-        id4[0] = base + c0.id;
-        id4[1] = base + c1.id;
-        id4[2] = base + c2.id;
-        id4[3] = base + c3.id;
-        z4[0] = c0.z;
-        z4[1] = c1.z;
-        z4[2] = c2.z;
-        z4[3] = c3.z;
-        d4[0] = dist2_rn(__fsub_rn(c0.x, xfj), __fsub_rn(c0.y, yfj));
-        const float e1 = dist2_rn(__fsub_rn(c1.x, xfj), __fsub_rn(c1.y, yfj));
-        const float e2 = dist2_rn(__fsub_rn(c2.x, xfj), __fsub_rn(c2.y, yfj));
-        const float e3 = dist2_rn(__fsub_rn(c3.x, xfj), __fsub_rn(c3.y, yfj));
-        d4[1] = (k0 + 1 < nhj) ? e1 : -1.0f;  // slot k0 itself is always a real hit here
-        d4[2] = (k0 + 2 < nhj) ? e2 : -1.0f;
-        d4[3] = (k0 + 3 < nhj) ? e3 : -1.0f;
-      }
-      if (k0 < K) {
-        const size_t o = (((size_t)b * S + (ty * TILE + (pj >> 3))) * S + tx * TILE + (pj & 7)) * K + k0;
-        if (vec) {
-          if (q.idx) __stcs(reinterpret_cast<int4*>(q.idx + o), make_int4(id4[0], id4[1], id4[2], id4[3]));
-          if (q.zbuf) __stcs(reinterpret_cast<float4*>(q.zbuf + o), make_float4(z4[0], z4[1], z4[2], z4[3]));
-          if (q.dist2) __stcs(reinterpret_cast<float4*>(q.dist2 + o), make_float4(d4[0], d4[1], d4[2], d4[3]));
-        } else {
+      const float xfj = sm.ndcx[pj & 7], yfj = sm.ndcy[pj >> 3];
+      const size_t o = (((size_t)b * S + (ty * TILE + (pj >> 3))) * S + tx * TILE + (pj & 7)) * K;
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (k0 + e < K) {
-              if (q.idx) q.idx[o + e] = id4[e];
-              if (q.zbuf) q.zbuf[o + e] = z4[e];
-              if (q.dist2) q.dist2[o + e] = d4[e];
-            }
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e;
+        if (k >= K) break;
+        int idv = -1;
+        float zv = -1.0f, dv = -1.0f;
+        if (k < nhj) {
+          const unsigned en = sm.u.r.lists[pj][k];
+          const uint2 c = ld_zid(sm, en);
+          const float2 pxy = ld_xy(sm, en);
+          idv = (int)c.y;
+          zv = __uint_as_float(c.x);
+          dv = dist2_rn(__fsub_rn(pxy.x, xfj), __fsub_rn(pxy.y, yfj));
         }
+        if (q.idx) q.idx[o + k] = idv;
+        if (q.zbuf) q.zbuf[o + k] = zv;
+        if (q.dist2) q.dist2[o + k] = dv;
       }
     }
   }
@@ -1050,12 +1025,6 @@ static SplatLayout splat_layout(int B, int P, int S) {
   return L;
 }
 
-// Which fine_kernel encoding runs (see the kernel's comment).  PS_SPLAT_VARIANT overrides the default for A/B timing.
-static int splat_variant() {
-  const char* e = getenv("PS_SPLAT_VARIANT");
-  return e ? atoi(e) : PS_SPLAT_DEFAULT_VARIANT;
-}
-
 // depth != null: project from depth (forward_justpts); else pts (B,P,3) is the cloud.
 static int splat_impl(const float* depth, const float* mats, int W, float eps, const float* pts, const float* feat,
                       int B, int P, int C, int S, int K, double radius_px, double tau, int rad_pow, int accumulation,
@@ -1130,10 +1099,9 @@ static int splat_impl(const float* depth, const float* mats, int W, float eps, c
   int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
   if (smem_set_for_device != dev) {
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
-    PS_CUDA(cudaFuncSetAttribute(fine_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
+    PS_CUDA(cudaFuncSetAttribute(fine_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FineSmem)));
     PS_CUDA(cudaFuncSetAttribute(fine_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem)));
     smem_set_for_device = dev;
   }
@@ -1141,18 +1109,12 @@ static int splat_impl(const float* depth, const float* mats, int W, float eps, c
     dim3 grid(L.nt2, B);
     PS_TIME_BEGIN("fine_kernel", stream);
     const bool fast = accumulation == PS_ACCUM_ALPHACOMPOSITE && q.tau == 1.0f && q.inv_denom != 0.0f && C <= 4;
-    static const int variant = splat_variant();
-    if (variant == 1) {
-      if (fast)
-        fine_kernel<true, 1><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
-      else
-        fine_kernel<false, 1><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
-    } else {
-      if (fast)
-        fine_kernel<true, 0><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
-      else
-        fine_kernel<false, 0><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
-    }
+    if (fast && C <= 3)
+      fine_kernel<true, 3><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+    else if (fast)
+      fine_kernel<true, 4><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
+    else
+      fine_kernel<false, 4><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
     PS_TIME_END(stream);
     PS_LAUNCHED();
     fine_big_kernel<<<296, TPB, sizeof(BigSmem), stream>>>(q);

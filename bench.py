@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128,
                     help="images (= views) per step per GPU.  The sampler's serial levels cost the same at any batch, "
-                         "so throughput is quoted at 128; 32 (BASELINE configs[4]'s per-GPU share) is profiles/r01_bench_b32_final.json")
+                         "so throughput is quoted at 128; 32 (BASELINE configs[4]'s per-GPU share) is profiles/r01_bench_b32_s5.json")
     ap.add_argument("--cpu-tokens", type=int, default=4, help="sampler tokens timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -79,8 +79,8 @@ def workload_config(args, world):
         "weights": "seeded random init of the reference architecture (pixelsynth_b200/synthetic.py)",
         "l2_policy": "activations + sampler cache per step (> 1 GB at batch 32) exceed the 126 MB L2; no explicit flush",
         "batch_note": "the outpaint sampler's sampled levels are a serial chain whose latency does not depend on the batch, "
-                      "so views/s grows with the batch until the convolutions dominate; measured 996 views/s at 32 and 1833 at 128 "
-                      "per GPU (profiles/r01_bench_b32_final.json, r01_bench_b128_final.json)",
+                      "so views/s grows with the batch until the convolutions dominate; measured 1007 views/s at 32, 1489 at 64 and 1946 "
+                      "at 128 per GPU (profiles/r01_bench_b{32,64,128}_s5.json)",
         "parallelism": "images sharded across ranks; one NCCL broadcast of the source images at job start" if world > 1
                        else "single GPU",
     }
@@ -235,10 +235,32 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_supervised():
+    """Single-GPU runs measure in a child process and re-measure (at most twice) when the child dies: a CUDA fault
+    ("unspecified launch failure" of the outpaint sampler at batch 128, intermittent) kills the CUDA
+    context, so it cannot be retried in-process.  The JSON line reports how many attempts it took (`attempts`)."""
+    rc = 1
+    for attempt in (1, 2, 3):
+        p = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:],
+                           env=dict(os.environ, PS_BENCH_CHILD="1"), stdout=subprocess.PIPE, text=True)
+        rc = p.returncode
+        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if rc == 0 and lines:
+            line = json.loads(lines[-1])
+            line["attempts"] = attempt
+            print(json.dumps(line), flush=True)
+            return 0
+        sys.stderr.write("bench.py: attempt %d failed (exit code %d)%s\n" % (attempt, rc, ", measuring again" if attempt < 3 else ""))
+    raise SystemExit(rc if rc else 1)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+
+    if os.environ.get("PS_BENCH_CHILD") != "1" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        return run_supervised()
 
     import torch
     import torch.distributed as dist
@@ -373,7 +395,7 @@ def main():
         "splat fine_kernel": {"bound": "hbm", "achieved": BYTES_PER_VIEW_SPLAT_FUSED * B / (per_step["fine_kernel"][0] * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s", "ms_per_step": per_step["fine_kernel"][0],
                               "note": "maps suppressed inside the pipeline (1.90 MB/view: compute bound); the map-emitting "
-                                      "mode (69.0 MB/view) reaches 0.455 of HBM peak, DESIGN.md section 4"},
+                                      "mode (69.0 MB/view) is the line below, measured in the same run; DESIGN.md section 4"},
         "lmconv_tc_kernel": {"bound": "tensor", "achieved": FLOP_PER_CELL * cells_processed / (per_step["lmconv_tc_kernel"][0] * 1e-3) / 1e12,
                                  "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["lmconv_tc_kernel"][0],
                                  "cells_processed_per_step": cells_processed, "cells_sampled_per_step": cells_sampled,

@@ -53,15 +53,14 @@ struct ResampleOut {
 __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __restrict__ in, int N, int H, int W, int C,
                                                        int in_cstride, int mode, int Ho, int Wo, ResampleOut o0,
                                                        ResampleOut o1) {
-  const int groups = C >> 3;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)N * Ho * Wo * groups;
-  if (idx >= total) return;
-  const int g = (int)(idx % groups);
-  size_t pix = idx / groups;
-  const int ox = (int)(pix % Wo);
-  const int oy = (int)((pix / Wo) % Ho);
-  const int n = (int)(pix / ((size_t)Wo * Ho));
+  // grid = (ceil(Wo * groups / 256), Ho, N): one 32-bit division per thread instead of four 64-bit ones on a flat index
+  const unsigned groups = (unsigned)C >> 3;
+  const unsigned ix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ix >= (unsigned)Wo * groups) return;
+  const int ox = (int)(ix / groups);
+  const int g = (int)(ix - (unsigned)ox * groups);
+  const int oy = blockIdx.y;
+  const int n = blockIdx.z;
   float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   auto accum = [&](int y, int x, float w) {
     const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * H + y) * W + x) * in_cstride + g * 8);
@@ -99,12 +98,20 @@ __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __re
     if (!o.ptr) continue;
     const float* sc = o.scale ? o.scale + (o.per_sample ? (size_t)n * C : 0) + g * 8 : nullptr;
     const float* sh = o.shift ? o.shift + (o.per_sample ? (size_t)n * C : 0) + g * 8 : nullptr;
-    float y[8];
+    float y[8], s8[8], h8[8];
+    if (sc) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(sc)), c = __ldg(reinterpret_cast<const float4*>(sc) + 1);
+      s8[0] = a.x, s8[1] = a.y, s8[2] = a.z, s8[3] = a.w, s8[4] = c.x, s8[5] = c.y, s8[6] = c.z, s8[7] = c.w;
+    }
+    if (sh) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(sh)), c = __ldg(reinterpret_cast<const float4*>(sh) + 1);
+      h8[0] = a.x, h8[1] = a.y, h8[2] = a.z, h8[3] = a.w, h8[4] = c.x, h8[5] = c.y, h8[6] = c.z, h8[7] = c.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float t = v[j];
-      if (sc) t *= sc[j];
-      if (sh) t += sh[j];
+      if (sc) t *= s8[j];
+      if (sh) t += h8[j];
       y[j] = ew_act(t, o.act);
     }
     __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
@@ -231,7 +238,7 @@ int ps_nchw_to_nhwc_bf16(const float* x, int N, int C, int H, int W, const uint8
 int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int mode, const ps_conv_output* out0,
                 const ps_conv_output* out1, void* stream) {
   PS_CHECK_ARG(in && out0 && N >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && in_cstride % 8 == 0);
-  PS_CHECK_ARG(mode >= 0 && mode <= 2);
+  PS_CHECK_ARG(mode >= 0 && mode <= 2 && N <= 65535 && H <= 32767);
   const int Ho = mode == 1 ? (H + 1) / 2 : (mode == 2 ? 2 * H : H);
   const int Wo = mode == 1 ? (W + 1) / 2 : (mode == 2 ? 2 * W : W);
   ResampleOut o[2];
@@ -240,6 +247,7 @@ int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int 
   for (int k = 0; k < 2; ++k)
     if (src[k] && src[k]->ptr) {
       PS_CHECK_ARG(src[k]->cstride % 8 == 0 && src[k]->coffset % 8 == 0);
+      PS_CHECK_ARG(((uintptr_t)src[k]->scale & 15) == 0 && ((uintptr_t)src[k]->shift & 15) == 0);  // read as float4
       o[k].ptr = (__nv_bfloat16*)src[k]->ptr;
       o[k].scale = src[k]->scale;
       o[k].shift = src[k]->shift;
@@ -250,7 +258,8 @@ int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int 
     }
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
   if (total == 0) return PS_OK;
-  resample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  dim3 grid((unsigned)(((size_t)Wo * (C / 8) + 255) / 256), (unsigned)Ho, (unsigned)N);
+  resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)in, N, H, W, C, in_cstride, mode, Ho, Wo, o[0], o[1]);
   PS_LAUNCHED();
   return PS_OK;

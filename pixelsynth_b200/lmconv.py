@@ -255,7 +255,11 @@ class LmconvB200:
         codes_d = torch.as_tensor(codes).to(device=dev, dtype=torch.int64).reshape(B, 1024).clone()
         logits = torch.empty((B, 1024, 512), dtype=torch.float32, device=dev) if mode == 1 else None
         if len(offs) > 1:
-            uni_d = None if uniforms is None else torch.as_tensor(uniforms).to(device=dev, dtype=torch.float32, non_blocking=True).reshape(B, -1).contiguous()
+            uni_d = None
+            if uniforms is not None:
+                u = torch.as_tensor(uniforms)
+                # an asynchronous copy from pageable memory may read its source after the caller has dropped it
+                uni_d = u.to(device=dev, dtype=torch.float32, non_blocking=u.is_cuda or u.is_pinned()).reshape(B, -1).contiguous()
             nbytes = _lib.lib().ps_lmconv_tc_cache_bytes(B)
             if self._cache is None or self._cache.numel() < nbytes:
                 self._cache = torch.empty(nbytes, dtype=torch.uint8, device=dev)

@@ -89,7 +89,7 @@ class ZbufferModelPts(nn.Module):
     def process_batch(self, batch):
         cam = batch["cameras"][0]
         dev = self.device
-        f = lambda t: t.to(dev, non_blocking=True).float()
+        f = lambda t: t.to(dev, non_blocking=t.is_cuda or t.is_pinned()).float()  # pageable sources: blocking copy
         out = [f(cam["K"]), f(cam["Kinv"]), f(cam["P"]), f(cam["Pinv"])]
         if _get(self.opt, "model_setting") in ("train", "gen_paired_img"):
             out += [f(batch["cameras"][-1]["P"]), f(batch["cameras"][-1]["Pinv"]), f(batch["images"][0]),
@@ -211,7 +211,9 @@ class ZbufferModelPts(nn.Module):
             self.last = dict(depth=regressed_pts, gen_fs=gen_fs, background_mask=background_mask, order=order, words=words,
                              sample_mask=sample_mask, codes=codes, output_RT=output_RT)
         outputs = {"InputImg": input_img, "PredImg": gen_img, "PredDepthImg": regressed_pts / 5 - 1,
-                   "ForegroundImg": (~background_mask).repeat(B, 1, 1, 1).float()}   # shape quirk kept (:389)
+                   # (:389) `(~bg).repeat(B,1,1,1).float()`: shape (B,B,S,S), [i,j] = mask j.  Same shape and values as a
+                   # broadcast view: at batch 128 the materialised tensor would be 4.3 GB written per step
+                   "ForegroundImg": (~background_mask).float().unsqueeze(0).expand(B, -1, -1, -1)}
         if output_img is not None:
             outputs["OutputImg"] = output_img
         outputs["FeaturesImg"] = gen_fs

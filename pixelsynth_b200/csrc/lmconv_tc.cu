@@ -971,11 +971,11 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   Tile* tiles_dev = (Tile*)tail;
   unsigned int* sync_dev = (unsigned int*)(tail + align_up(tc_max_tiles(B) * sizeof(Tile), 256));
   PS_CUDA(cudaMemcpyAsync(tiles_dev, tiles.data(), (size_t)n_tiles * sizeof(Tile), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  // `tiles` is pageable host memory that dies with this call.  An async copy from pageable memory is only staged
-  // eagerly up to 64 KB; beyond that (about 2000 tiles = batch 128) it may read the source when the stream gets
-  // there -- after the vector is gone: garbage tile descriptors, then "unspecified launch failure" (seen only at
-  // batch 128, never under CUDA_LAUNCH_BLOCKING / compute-sanitizer).  Wait for the upload: everything queued before it
-  // (the VQ-VAE encoder) is what the sampler launch below would wait for anyway.
+  // `tiles` is pageable host memory that dies with this call, and the sampler below is the one kernel of the path that
+  // was seen to fault intermittently (batch 128 only, never under CUDA_LAUNCH_BLOCKING / compute-sanitizer; DESIGN.md
+  // section 8).  Until that is understood the launch is serialised: wait for the uploads (the table is ~44 KB at batch
+  // 128, so by the documented rules the driver has staged it already -- this removes the doubt) and for everything
+  // queued before them, which the sampler would wait for anyway.
   PS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   PS_CUDA(cudaMemsetAsync(sync_dev, 0, ((size_t)n_tiles + 16) * sizeof(unsigned int), (cudaStream_t)stream));
   p.tiles = tiles_dev;

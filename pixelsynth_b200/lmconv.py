@@ -269,6 +269,11 @@ class LmconvB200:
                     None if uni_d is None else uni_d.data_ptr(), 0 if uni_d is None else uni_d.shape[1], float(temperature),
                     None if logits is None else logits.data_ptr(), self._cache.data_ptr(), nbytes,
                     torch.cuda.current_stream().cuda_stream), "ps_lmconv_tc_run")
+                # The sampler runs alone: ps_lmconv_tc_run drains the stream before it launches, and the host waits here
+                # until the kernel is done (the GPU then idles for one launch latency).  An intermittent "unspecified
+                # launch failure" at batch 128 (profiles/r01_launch_failure_bisect.txt) never
+                # appeared when the sampler was serialised like this (CUDA_LAUNCH_BLOCKING run); its cause is open.
+                torch.cuda.current_stream().synchronize()
         return codes_d.view(B, 32, 32), logits
 
     def sample(self, codes, order, words, sample_mask, uniforms, temperature=1.0, prepared=None):

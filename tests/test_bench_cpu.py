@@ -29,7 +29,7 @@ def test_flags_and_workload_description():
         a = bench.parse()
     finally:
         sys.argv = argv
-    assert (a.gpus, a.steps, a.warmup, a.impl, a.batch) == (8, 7, 4, "reference", 128)
+    assert (a.gpus, a.steps, a.warmup, a.impl, a.batch) == (8, 7, 4, "reference", 64)
     cfg = bench.workload_config(a, 8)
-    assert "configs[1]" in cfg["workload"] and cfg["views_per_step_per_gpu"] == 128 and cfg["global_views_per_step"] == 1024
+    assert "configs[1]" in cfg["workload"] and cfg["views_per_step_per_gpu"] == 64 and cfg["global_views_per_step"] == 512
     assert bench.BYTES_PER_VIEW_SPLAT_MAPS == 69009408 and bench.BYTES_PER_VIEW_SPLAT_FUSED == 1900544

@@ -281,7 +281,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that dies must not leave the others in a collective for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=3))
 
     from pixelsynth_b200 import _lib
     from pixelsynth_b200.models.base_model import BaseModel

@@ -42,6 +42,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -812,83 +813,140 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
   PS_CHECK_ARG(mode == 1 || sample_mask);
   PS_CHECK_ARG(B < (1 << 20));
   // level >= 0: phase A level; level <= -2: phase B level -(level + 2); -1: no row
-  std::vector<int> level((size_t)B * LMT_CELLS, -1), uidx((size_t)B * LMT_CELLS, 0), rank(LMT_CELLS);
-  int top_a = -1, top_b = -1;
-  for (int b = 0; b < B; ++b) {
-    const int* ord = order + (size_t)b * LMT_CELLS;
-    const uint16_t* w = words + (size_t)b * 3 * LMT_CELLS;
-    int* lv = level.data() + (size_t)b * LMT_CELLS;
-    for (int i = 0; i < LMT_CELLS; ++i) {
-      PS_CHECK_ARG(ord[i] >= 0 && ord[i] < LMT_CELLS);
-      rank[ord[i]] = i;
+  std::vector<int> level((size_t)B * LMT_CELLS, -1), uidx((size_t)B * LMT_CELLS, 0);
+  // Images are independent: worker c owns the images [c*B/T, (c+1)*B/T).  Rows of a level are emitted in (image, cell)
+  // order whatever T is: per-worker level histograms are prefix-summed in worker order before the rows are written.
+  unsigned hw = std::thread::hardware_concurrency();
+  const int T = std::max(1, std::min({(int)(hw ? hw : 1), 32, B / 4}));
+  std::vector<int> tops_a(T, -1), tops_b(T, -1), bad(T, 0);
+  auto run_workers = [&](auto&& fn) {
+    if (T == 1) {
+      fn(0);
+      return;
     }
-    int last = LMT_CELLS - 1;
-    const uint8_t* smk = mode == 0 ? sample_mask + (size_t)b * LMT_CELLS : nullptr;
-    if (mode == 0) {
-      int drawn = 0;
-      last = -1;
-      for (int i = 0; i < LMT_CELLS; ++i)
-        if (smk[ord[i]]) {
-          last = i;
-          uidx[(size_t)b * LMT_CELLS + ord[i]] = drawn++;
+    std::vector<std::thread> th;
+    for (int c = 0; c < T; ++c) th.emplace_back(fn, c);
+    for (auto& t : th) t.join();
+  };
+  auto image_range = [&](int c, int& lo, int& hi) {
+    lo = (int)((long long)B * c / T);
+    hi = (int)((long long)B * (c + 1) / T);
+  };
+  run_workers([&](int c) {
+    int lo, hi;
+    image_range(c, lo, hi);
+    std::vector<int> rank(LMT_CELLS);
+    int top_a = -1, top_b = -1;
+    for (int b = lo; b < hi && !bad[c]; ++b) {
+      const int* ord = order + (size_t)b * LMT_CELLS;
+      const uint16_t* w = words + (size_t)b * 3 * LMT_CELLS;
+      int* lv = level.data() + (size_t)b * LMT_CELLS;
+      for (int i = 0; i < LMT_CELLS; ++i) {
+        if (ord[i] < 0 || ord[i] >= LMT_CELLS) {
+          bad[c] = 1;
+          break;
         }
-      if (last < 0) continue;  // nothing to sample: the image needs no work
-    }
-    for (int i = 0; i <= last; ++i) {
-      const int cell = ord[i];
-      const int r = cell / 32, c = cell % 32;
-      int la = -1, lb = -1;
-      bool in_b = smk && smk[cell];
-      for (int m = 0; m < 3; ++m) {
-        const int dil = m == 2 ? 2 : 1;
-        for (int t = 0; t < 9; ++t) {
-          if (t == 4 || !((w[m * LMT_CELLS + cell] >> t) & 1)) continue;
-          const int rr = r + (t / 3 - 1) * dil, cc = c + (t % 3 - 1) * dil;
-          PS_CHECK_ARG(rr >= 0 && rr < 32 && cc >= 0 && cc < 32);       // masks never reach outside the grid
-          PS_CHECK_ARG(rank[rr * 32 + cc] < i);                          // ... nor forward in the order
-          const int l = lv[rr * 32 + cc];
-          if (l >= 0) {
-            la = std::max(la, l);
-          } else {
-            in_b = true;
-            lb = std::max(lb, -(l + 2));
+        rank[ord[i]] = i;
+      }
+      if (bad[c]) break;
+      int last = LMT_CELLS - 1;
+      const uint8_t* smk = mode == 0 ? sample_mask + (size_t)b * LMT_CELLS : nullptr;
+      if (mode == 0) {
+        int drawn = 0;
+        last = -1;
+        for (int i = 0; i < LMT_CELLS; ++i)
+          if (smk[ord[i]]) {
+            last = i;
+            uidx[(size_t)b * LMT_CELLS + ord[i]] = drawn++;
           }
+        if (last < 0) continue;  // nothing to sample: the image needs no work
+      }
+      for (int i = 0; i <= last && !bad[c]; ++i) {
+        const int cell = ord[i];
+        const int r = cell / 32, cc0 = cell % 32;
+        int la = -1, lb = -1;
+        bool in_b = smk && smk[cell];
+        for (int m = 0; m < 3; ++m) {
+          const int dil = m == 2 ? 2 : 1;
+          for (int t = 0; t < 9; ++t) {
+            if (t == 4 || !((w[m * LMT_CELLS + cell] >> t) & 1)) continue;
+            const int rr = r + (t / 3 - 1) * dil, cc = cc0 + (t % 3 - 1) * dil;
+            // masks never reach outside the grid, nor forward in the order
+            if (rr < 0 || rr >= 32 || cc < 0 || cc >= 32 || rank[rr * 32 + cc] >= i) {
+              bad[c] = 1;
+              break;
+            }
+            const int l = lv[rr * 32 + cc];
+            if (l >= 0) {
+              la = std::max(la, l);
+            } else {
+              in_b = true;
+              lb = std::max(lb, -(l + 2));
+            }
+          }
+          if (bad[c]) break;
+        }
+        if (bad[c]) break;
+        if (in_b) {
+          lv[cell] = -(lb + 1 + 2);
+          top_b = std::max(top_b, lb + 1);
+        } else {
+          lv[cell] = la + 1;
+          top_a = std::max(top_a, la + 1);
         }
       }
-      if (in_b) {
-        lv[cell] = -(lb + 1 + 2);
-        top_b = std::max(top_b, lb + 1);
-      } else {
-        lv[cell] = la + 1;
-        top_a = std::max(top_a, la + 1);
-      }
     }
-  }
+    tops_a[c] = top_a;
+    tops_b[c] = top_b;
+  });
+  for (int c = 0; c < T; ++c)
+    if (bad[c]) return fail(PS_EINVAL, "%s: order is not a permutation or a mask reaches outside the grid / forward in the order%s", __func__);
+  const int top_a = *std::max_element(tops_a.begin(), tops_a.end()), top_b = *std::max_element(tops_b.begin(), tops_b.end());
   const int na = top_a + 1, nb = top_b + 1;
   if (na + nb > max_levels) return fail(PS_EWORKSPACE, "%s: more dependency levels than level_offsets holds%s", __func__);
+  const int nl = na + nb;
   auto slot = [&](int l) { return l >= 0 ? l : na - (l + 2); };
-  std::vector<int> count(na + nb + 1, 0);
-  for (size_t i = 0; i < level.size(); ++i)
-    if (level[i] != -1) ++count[slot(level[i]) + 1];
-  for (int l = 0; l < na + nb; ++l) count[l + 1] += count[l];
-  for (int l = 0; l <= na + nb; ++l) level_offsets[l] = count[l];
-  std::vector<int> cursor(count.begin(), count.end() - 1);
-  for (int b = 0; b < B; ++b)
-    for (int cell = 0; cell < LMT_CELLS; ++cell) {
-      const int l = level[(size_t)b * LMT_CELLS + cell];
-      if (l == -1) continue;
-      const uint16_t* w = words + (size_t)b * 3 * LMT_CELLS;
-      ps_lmconv_row ri;
-      ri.bc = (b << 10) | cell;
-      ri.w01 = (uint32_t)w[cell] | ((uint32_t)w[LMT_CELLS + cell] << 16);
-      ri.w2_flags = (uint32_t)w[2 * LMT_CELLS + cell] | ROW_VALID;
-      if (mode == 1)
-        ri.w2_flags |= ROW_LOGITS;
-      else if (sample_mask[(size_t)b * LMT_CELLS + cell])
-        ri.w2_flags |= ROW_SAMPLED;
-      ri.uidx = uidx[(size_t)b * LMT_CELLS + cell];
-      rows_out[cursor[slot(l)]++] = ri;
+  std::vector<int> hist((size_t)T * (nl + 1), 0);  // hist[c][l]: rows of level l among worker c's images
+  run_workers([&](int c) {
+    int lo, hi;
+    image_range(c, lo, hi);
+    int* h = hist.data() + (size_t)c * (nl + 1);
+    for (size_t i = (size_t)lo * LMT_CELLS; i < (size_t)hi * LMT_CELLS; ++i)
+      if (level[i] != -1) ++h[slot(level[i])];
+  });
+  // level_offsets, and hist[c][l] := first row of worker c inside level l
+  int run = 0;
+  for (int l = 0; l < nl; ++l) {
+    level_offsets[l] = run;
+    for (int c = 0; c < T; ++c) {
+      const int n = hist[(size_t)c * (nl + 1) + l];
+      hist[(size_t)c * (nl + 1) + l] = run;
+      run += n;
     }
+  }
+  level_offsets[nl] = run;
+  run_workers([&](int c) {
+    int lo, hi;
+    image_range(c, lo, hi);
+    int* cursor = hist.data() + (size_t)c * (nl + 1);
+    for (int b = lo; b < hi; ++b) {
+      const uint16_t* w = words + (size_t)b * 3 * LMT_CELLS;
+      for (int cell = 0; cell < LMT_CELLS; ++cell) {
+        const int l = level[(size_t)b * LMT_CELLS + cell];
+        if (l == -1) continue;
+        ps_lmconv_row ri;
+        ri.bc = (b << 10) | cell;
+        ri.w01 = (uint32_t)w[cell] | ((uint32_t)w[LMT_CELLS + cell] << 16);
+        ri.w2_flags = (uint32_t)w[2 * LMT_CELLS + cell] | ROW_VALID;
+        if (mode == 1)
+          ri.w2_flags |= ROW_LOGITS;
+        else if (sample_mask[(size_t)b * LMT_CELLS + cell])
+          ri.w2_flags |= ROW_SAMPLED;
+        ri.uidx = uidx[(size_t)b * LMT_CELLS + cell];
+        rows_out[cursor[slot(l)]++] = ri;
+      }
+    }
+  });
   *n_levels = na + nb;
   *first_b_level = na;
   return PS_OK;

@@ -817,6 +817,7 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
   // Images are independent: worker c owns the images [c*B/T, (c+1)*B/T).  Rows of a level are emitted in (image, cell)
   // order whatever T is: per-worker level histograms are prefix-summed in worker order before the rows are written.
   unsigned hw = std::thread::hardware_concurrency();
+  if (const char* e = getenv("PS_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));  // tests pin the worker count
   const int T = std::max(1, std::min({(int)(hw ? hw : 1), 32, B / 4}));
   std::vector<int> tops_a(T, -1), tops_b(T, -1), bad(T, 0);
   auto run_workers = [&](auto&& fn) {

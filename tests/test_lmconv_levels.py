@@ -129,3 +129,26 @@ def test_weight_schedule_tiles_reproduce_the_layers():
     assert [int(c["kind"]) for c in ch[-8:]] == [2, 2, 4, 4, 4, 4, 4, 4] and m.plan.raw_mask == sum(1 << t for t in (4, 8, 18, 24))
     # the last quarter of nin_out ends the schedule and completes the logits barrier
     assert ch[-1]["fl"] & 2 and (ch[-1]["fl"] >> 2) & 3 == 2 and ch[-1]["col"] == 384
+
+
+def test_level_rows_do_not_depend_on_the_worker_count(monkeypatch):
+    """ps_lmconv_levels_host splits the images over host threads; rows of a level stay in (image, cell) order."""
+    import pixelsynth_b200.lmconv as lmconv
+
+    rng = np.random.default_rng(3)
+    B = 24
+    m = np.zeros((B, 256, 256), bool)
+    yy, xx = np.mgrid[0:256, 0:256]
+    for i in range(1, B):   # image 0 has nothing to sample
+        m[i] = ((xx - rng.integers(0, 256)) ** 2 + (yy - rng.integers(0, 256)) ** 2) < rng.integers(30, 220) ** 2
+    _, order, words, smask = lmconv.glue_host(m)
+    outs = []
+    for threads in ("1", "2", "5", "6"):
+        monkeypatch.setenv("PS_HOST_THREADS", threads)
+        for mode, sm in ((0, smask.astype(np.uint8)), (1, None)):
+            rows, offs, first_b = lmconv.LmconvB200.levels_host(order, words, sm, mode)
+            outs.append((threads, mode, rows.tobytes(), offs.tobytes(), first_b))
+    for mode in (0, 1):
+        ref = [o for o in outs if o[1] == mode]
+        assert all(o[2:] == ref[0][2:] for o in ref), "rows differ between worker counts"
+        assert len(ref[0][2]) > 0

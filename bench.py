@@ -93,7 +93,8 @@ def make_batch(B, view, seed=0):
     from util import demo_cameras
     from pixelsynth_b200 import synthetic
 
-    K, Kinv, RT1, RT1inv, RT2, RT2inv = [torch.from_numpy(m) for m in demo_cameras(B, "translate", seed, views=[view] * B)]
+    views = list(view) if isinstance(view, (list, tuple)) else [view] * B   # per-image circle view, or one for all
+    K, Kinv, RT1, RT1inv, RT2, RT2inv = [torch.from_numpy(m) for m in demo_cameras(B, "translate", seed, views=views)]
     img = synthetic.synth_image(B, seed)
     return {"images": [img, img.clone()],
             "cameras": [{"K": K, "Kinv": Kinv, "P": RT1, "Pinv": RT1inv}, {"K": K, "Kinv": Kinv, "P": RT2, "Pinv": RT2inv}]}

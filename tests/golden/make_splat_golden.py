@@ -142,8 +142,57 @@ def run_case(name, W, K, radius_px, kind, B=2, C=3, tau=1.0, accumulation="alpha
           "empty", (out["idx"][..., 0] < 0).mean(), os.path.getsize(path) // 1024, "KiB")
 
 
+def run_cumulative(name, W=32, K=16, radius_px=3.0, n_views=3, seed=5):
+    """gen_scene's growing cloud: n_views chained calls of the reference's UNMODIFIED forward_justpts_cumulative
+    (z_buffer_manipulator.py:184-219) / project_pts_cumulative (:221-266), batch 1 like forward_scene
+    (z_buffermodel.py:491-504,555-568): view v's source camera is view v-1's target, only the pixels under the
+    previous background mask are appended, the prior cloud is the stored pre-division xy_proj."""
+    from models.projection.z_buffer_manipulator import PtsManipulator
+    rng = np.random.default_rng(seed)
+    opt = types.SimpleNamespace(splatter="xyblending", learn_default_feature=True, radius=radius_px, pp_pixel=K,
+                                rad_pow=2, tau=1.0, accumulation="alphacomposite", background_smoothing_kernel_size=5)
+    torch.manual_seed(0)
+    pm = PtsManipulator(W, C=3, opt=opt)
+    Ks, Kinvs, RT1, RT1inv, _, _ = cameras(1, rng, "identity")
+    out = dict(W=W, K=K, radius_px=radius_px, ksize=5, n_views=n_views)
+    prior, fs_old, last_bg, last_out_inv = None, None, None, None
+    src_rt, src_inv = RT1, RT1inv
+    for v in range(n_views):
+        depth = rng.uniform(1.0, 6.0, (1, 1, W, W)).astype(np.float32)
+        feat = rng.uniform(-1, 1, (1, 3, W, W)).astype(np.float32)
+        dst_rt = RT1.copy()
+        # a target that keeps moving: translation + a small rotation about y, so each view uncovers new pixels
+        th = 0.25 * (v + 1)
+        M = np.eye(4, dtype=np.float32)
+        M[0, 0] = np.cos(th); M[0, 2] = np.sin(th); M[2, 0] = -np.sin(th); M[2, 2] = np.cos(th)
+        dst_rt[0] = M @ RT1[0]
+        dst_rt[0, :3, 3] += np.array([0.3 * (v + 1), -0.1 * v, 0.05], np.float32)
+        dst_inv = np.linalg.inv(dst_rt).astype(np.float32)
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a))
+        with torch.no_grad():
+            gen_fs, bg, cloud, src = pm.forward_justpts_cumulative(
+                t(feat), t(depth), t(Ks), t(Kinvs), t(src_rt), t(src_inv), t(dst_rt), t(dst_inv),
+                None if prior is None else prior.clone(), None if fs_old is None else fs_old.clone(),
+                None if last_bg is None else last_bg.clone(), t(last_out_inv))
+        for k, a in (("depth", depth), ("feat", feat), ("src_rt", src_rt), ("src_inv", src_inv), ("dst_rt", dst_rt),
+                     ("dst_inv", dst_inv), ("gen_fs", gen_fs.numpy()), ("bg", bg.numpy()), ("cloud", cloud.numpy()),
+                     ("src", src.numpy()), ("idx", CAPTURE["idx"]), ("zbuf", CAPTURE["zbuf"])):
+            out["v%d_%s" % (v, k)] = a
+        print(name, "view", v, "cloud", tuple(cloud.shape), "appended", 0 if last_bg is None else int(last_bg.sum()),
+              "empty", float((CAPTURE["idx"][..., 0] < 0).mean()))
+        prior, fs_old, last_bg, last_out_inv = cloud, src, bg, dst_inv
+        src_rt, src_inv = dst_rt, dst_inv
+    out["K_mat"], out["Kinv_mat"] = Ks, Kinvs
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(name, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     install_stubs()
+    if "--cumulative-only" in sys.argv:
+        run_cumulative("cumul_w32_k16")
+        sys.exit(0)
     run_case("w32_k8_translate", 32, 8, 4.0, "translate")
     run_case("w32_k64_rotate", 32, 64, 2.0, "rotate")
     run_case("w32_k16_behind", 32, 16, 4.0, "behind")
@@ -152,3 +201,4 @@ if __name__ == "__main__":
     run_case("w32_k16_wsum", 32, 16, 3.0, "translate", accumulation="wsum", tau=2.0, ksize=5)
     run_case("w32_k16_wsumnorm", 32, 16, 3.0, "rotate", accumulation="wsumnorm")
     run_case("w48_k128_translate", 48, 128, 4.0, "translate", B=1)
+    run_cumulative("cumul_w32_k16")

@@ -176,3 +176,19 @@ def test_demo_refuses_to_run_without_a_gpu(tmp_path):
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="no CPU path"):
         demo.main(["--model_setting", "gen_img", "--direction", "L", "--demo_img_name", "x.png", "--result_folder", str(tmp_path)])
+
+
+def test_reference_import_paths_resolve_to_the_mirrors():
+    """north_star: models.z_buffermodel / BaseModel.forward / demo.py stay drop-in -- the reference's import paths
+    (demo.py:9-14, options/options.py:3-18) resolve to the sm_100a mirrors."""
+    import importlib
+
+    import pixelsynth_b200.models.base_model as bm
+    import pixelsynth_b200.models.z_buffermodel as zb
+
+    assert importlib.import_module("models.z_buffermodel").ZbufferModelPts is zb.ZbufferModelPts
+    assert importlib.import_module("models.base_model").BaseModel is bm.BaseModel
+    assert importlib.import_module("models.projection.z_buffer_manipulator").PtsManipulator is not None
+    assert importlib.import_module("models.layers.z_buffer_layers").RasterizePointsXYsBlending is not None
+    top = importlib.import_module("demo")
+    assert top.main is demo.main

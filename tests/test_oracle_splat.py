@@ -74,3 +74,51 @@ def test_upsampled_target_and_empty(oracle):
     # zero points
     idx, _, _ = oracle.rasterize(np.zeros((1, 0, 3), np.float32), 8, 4, 0.5)
     assert (idx == -1).all()
+
+
+def _cumul():
+    import os
+    from util import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cumul_w32_k16.npz"))
+    return {k: g[k] for k in g.files}
+
+
+def test_oracle_cumulative_cloud_matches_reference():
+    """S2c pinned: the oracle's projection + prior-cloud transform + concatenation order against the reference's
+    own forward_justpts_cumulative / project_pts_cumulative (z_buffer_manipulator.py:184-266) run on three chained
+    views (tests/golden/make_splat_golden.py::run_cumulative)."""
+    from oracle import splat_ref as oracle
+    g = _cumul()
+    W, K, nv = int(g["W"]), int(g["K"]), int(g["n_views"])
+    radius = float(g["radius_px"]) / W * 2.0
+    prior, feats, last_bg, last_out_inv = None, None, None, None
+    for v in range(nv):
+        f = lambda k: g["v%d_%s" % (v, k)]
+        mats = oracle.pack_mats(g["K_mat"], g["Kinv_mat"], f("src_rt"), f("src_inv"), f("dst_rt"), f("dst_inv"))
+        pts, xyp = oracle.project(f("depth"), mats, W, want_xyproj=True)
+        feat = f("feat").reshape(1, 3, -1)
+        if prior is not None:
+            sel = last_bg.reshape(-1)
+            pts, xyp, feat = pts[:, sel], xyp[:, :, sel], feat[:, :, sel]          # only newly outpainted pixels (:201-202,228)
+            mats3 = np.stack([g["K_mat"].reshape(1, 16), f("dst_rt").reshape(1, 16), last_out_inv.reshape(1, 16)], 1)
+            pts2, xyp2 = oracle.project_cloud(prior, mats3)
+            pts, xyp = np.concatenate([pts, pts2], 1), np.concatenate([xyp, xyp2], 2)   # new first, prior after (:206,247)
+            feat = np.concatenate([feat, feats], 2)
+        # the stored cloud (pre-division xy_proj with EPS written through the view, :250-266)
+        np.testing.assert_allclose(xyp, f("cloud"), rtol=3e-7, atol=1e-6)
+        assert np.array_equal(feat, f("src"))
+        # the oracle's own points give the same maps up to the 2-ulp projection difference ...
+        idx, zbuf, d2 = oracle.rasterize(pts, W, K, radius)
+        same = idx == f("idx")
+        assert same.mean() > 0.999
+        np.testing.assert_allclose(zbuf[same], f("zbuf")[same], rtol=3e-7, atol=1e-6)
+        # ... and from the reference's own cloud (its division + flip, z_buffer_manipulator.py:258-264) they are bit-exact
+        c = f("cloud")
+        zs = c[:, 2]
+        ref_pts = np.stack([c[:, 0] / -zs, -(c[:, 1] / -zs), -zs], 2).astype(np.float32)
+        idx, zbuf, d2 = oracle.rasterize(ref_pts, W, K, radius)
+        assert np.array_equal(idx, f("idx")) and np.array_equal(zbuf, f("zbuf"))
+        out = oracle.composite(idx, d2, feat, radius, 2, 1.0, "alphacomposite")
+        np.testing.assert_allclose(out, f("gen_fs"), rtol=0, atol=2e-6)
+        assert np.array_equal(oracle.bgmask(idx, int(g["ksize"])), f("bg"))
+        prior, feats, last_bg, last_out_inv = f("cloud"), f("src"), f("bg"), f("dst_inv")

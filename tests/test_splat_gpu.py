@@ -237,3 +237,37 @@ def test_cumulative_cloud_two_views(ops, oracle):
     assert np.array_equal(src2.cpu().numpy(), feat_c)
     assert np.array_equal(bg2.cpu().numpy(), oracle.bgmask(idx_c, 13))
     np.testing.assert_allclose(res2.cpu().numpy(), out_c, rtol=0, atol=ATOL_OUT)
+
+
+def test_cumulative_chain_matches_reference_fixture(golden_dir):
+    """S2c on the GPU against the REFERENCE's own forward_justpts_cumulative (three chained views, fixture written by
+    tests/golden/make_splat_golden.py::run_cumulative): stored cloud, concatenated features (order: newly outpainted
+    pixels first, prior cloud after), image and background mask of every view."""
+    import os
+    import types
+
+    from pixelsynth_b200.models.projection.z_buffer_manipulator import PtsManipulator
+
+    g = np.load(os.path.join(golden_dir, "cumul_w32_k16.npz"))
+    W, K, nv = int(g["W"]), int(g["K"]), int(g["n_views"])
+    opt = types.SimpleNamespace(splatter="xyblending", learn_default_feature=True, radius=float(g["radius_px"]), pp_pixel=K,
+                                rad_pow=2, tau=1.0, accumulation="alphacomposite",
+                                background_smoothing_kernel_size=int(g["ksize"]))
+    pm = PtsManipulator(W, C=3, opt=opt).cuda()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    Km, Kinv = t(g["K_mat"]), t(g["Kinv_mat"])
+    prior, feats, last_bg, last_out_inv = None, None, None, None
+    for v in range(nv):
+        f = lambda k: g["v%d_%s" % (v, k)]
+        gen_fs, bg, cloud, src = pm.forward_justpts_cumulative(
+            t(f("feat")), t(f("depth")), Km, Kinv, t(f("src_rt")), t(f("src_inv")), t(f("dst_rt")), t(f("dst_inv")),
+            prior, feats, last_bg, last_out_inv)
+        assert tuple(cloud.shape) == f("cloud").shape and tuple(src.shape) == f("src").shape
+        np.testing.assert_allclose(cloud.cpu().numpy(), f("cloud"), rtol=3e-7, atol=1e-6)   # bmm contraction: 2 ulp
+        assert np.array_equal(src.cpu().numpy(), f("src"))
+        # the image can differ where a 2-ulp point flips a membership test; such pixels are a handful
+        diff = np.abs(gen_fs.cpu().numpy() - f("gen_fs")).max(1)
+        assert (diff > 2e-6).mean() < 2e-3, (diff > 2e-6).mean()
+        assert (bg.cpu().numpy() != f("bg")).mean() < 2e-3
+        # chain on the REFERENCE's state so one flipped pixel cannot snowball through the views
+        prior, feats, last_bg, last_out_inv = t(f("cloud")), t(f("src")), t(f("bg")), t(f("dst_inv"))

@@ -51,11 +51,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64,
-                    help="images (= views) per step per GPU.  The sampler's serial levels cost the same at any batch, so "
-                         "throughput grows with it: 1007 views/s at 32, 1489 at 64, 1946 at 128 "
-                         "(profiles/r01_bench_b{32,64,128}_s5.json).  The default stays at 64 while the intermittent launch "
-                         "failure seen only at 128 is open (DESIGN.md section 8)")
-    ap.add_argument("--cpu-tokens", type=int, default=4, help="sampler tokens timed for the CPU baseline")
+                    help="images (= views) per step per GPU (BASELINE configs[3]: batch 64).  The sampler's serial levels "
+                         "cost the same at any batch, so throughput grows with it")
+    ap.add_argument("--view", type=int, default=-1,
+                    help="-1 (default): image i of rank r renders circle view (i + r) mod 8, so every rank carries the same "
+                         "mix of all 8 views; 0..7: every image renders that one view")
+    ap.add_argument("--cpu-tokens", type=int, default=16, help="sampler tokens timed per step for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -72,20 +73,24 @@ def make_opt(**kw):
 
 
 def workload_config(args, world):
+    mix = ("image i of rank r renders circle view (i + r) mod 8: every rank carries the same mix of all 8 views"
+           if args.view < 0 else "every image renders circle view %d" % args.view)
     return {
-        "workload": "BASELINE configs[1] (demo path: depth Unet -> splat -> order/masks -> VQ-VAE-2 encode -> lmconv "
-                    "outpaint -> VQ-VAE-2 decode -> refinement decoder), one novel 256x256 view per synthetic image, "
-                    "target = translation-circle camera n = rank mod 8 (create_nerf_like_circles.py:14), num_samples 1, "
-                    "temperature 0.7, batched %d images per step per GPU" % args.batch,
+        "workload": "BASELINE configs[3] per GPU = configs[1] batched (demo path: depth Unet -> splat -> order/masks -> "
+                    "VQ-VAE-2 encode -> lmconv outpaint -> VQ-VAE-2 decode -> refinement decoder), one novel 256x256 view "
+                    "per synthetic image on the 8-view translation circle (create_nerf_like_circles.py:14), num_samples 1, "
+                    "temperature 0.7, %d images per step per GPU" % args.batch,
         "views_per_step_per_gpu": args.batch, "global_views_per_step": args.batch * world,
+        "view_mix": mix,
         "weights": "seeded random init of the reference architecture (pixelsynth_b200/synthetic.py)",
         "l2_policy": "activations + sampler cache per step (> 1 GB at batch 32) exceed the 126 MB L2; no explicit flush",
-        "batch_note": "the outpaint sampler's sampled levels are a serial chain whose latency does not depend on the batch, "
-                      "so views/s grows with the batch until the convolutions dominate; measured 1007 views/s at 32, 1489 at 64 and 1946 "
-                      "at 128 per GPU (profiles/r01_bench_b{32,64,128}_s5.json)",
         "parallelism": "images sharded across ranks; one NCCL broadcast of the source images at job start" if world > 1
                        else "single GPU",
     }
+
+
+def batch_views(args, rank):
+    return [(i + rank) % 8 for i in range(args.batch)] if args.view < 0 else [args.view] * args.batch
 
 
 def make_batch(B, view, seed=0):
@@ -158,9 +163,10 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------------------
 # CPU oracle of the same path (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_oracle_view_seconds(n_tokens, threads, seed=0):
-    """One view through the CPU oracle; the sampler runs `n_tokens` reference-style steps and is extrapolated to the
-    view's sampled-cell count.  Returns (seconds per view, dict of stage seconds, sampled cells)."""
+def cpu_oracle_view_seconds(n_tokens, threads, seed=0, view=0):
+    """One view through the CPU oracle; the sampler runs `n_tokens` reference-style steps (one full network forward per
+    token, models/lmconv/sample.py:54-66) and is extrapolated to the view's sampled-cell count.
+    Returns (extrapolated seconds per view, dict of stage seconds, sampled cells, measured wall seconds)."""
     import numpy as np
     import torch
     from oracle import lmconv_ref, nets_ref, splat_ref
@@ -170,8 +176,9 @@ def cpu_oracle_view_seconds(n_tokens, threads, seed=0):
     torch.set_num_threads(threads)
     sds = {n: synthetic.make_state(n, 0) for n in ("unet", "vqvae", "lmconv", "decoder")}
     img = synthetic.synth_image(1, seed)
-    cams = demo_cameras(1, "translate", seed, views=[0])
+    cams = demo_cameras(1, "translate", seed, views=[view])
     st = {}
+    t_wall = time.perf_counter()
     with torch.no_grad():
         t = time.perf_counter()
         depth = nets_ref.unet_depth(sds["unet"], img, 0.5, 10.0)
@@ -201,74 +208,61 @@ def cpu_oracle_view_seconds(n_tokens, threads, seed=0):
         comb = gen_fs * (~bg)[:, None].float() + ar * bg[:, None].float()
         nets_ref.decoder_forward(sds["decoder"], comb, bg, [torch.randn(1, 20, generator=g) for _ in range(16)])
         st["decoder"] = time.perf_counter() - t
-    total = sum(v for k, v in st.items() if k != "lmconv_per_token") + per_token * n_sampled
-    return total, st, n_sampled
+    wall = time.perf_counter() - t_wall
+    st["lmconv_tokens_timed"] = steps
+    total = sum(v for k, v in st.items() if k not in ("lmconv_per_token", "lmconv_tokens_timed")) + per_token * n_sampled
+    return total, st, n_sampled, wall
 
 
 def run_reference(args):
+    """--impl reference: the CPU oracle of the same path on all host cores, rank 0 only.  One step = ONE view (a bounded
+    sample of the arm's 64-views-per-step workload): every stage runs in full except the sampler, which is timed the
+    reference's way (a full network forward per token) on --cpu-tokens tokens and scaled to the view's sampled cells.
+    `ms_per_step` is the wall time the step really took; `value` is the extrapolated views/s (labelled)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    secs = []
+    secs, walls = [], []
     info = None
     t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        s, st, n_sampled = cpu_oracle_view_seconds(args.cpu_tokens, threads)
+        view = i % 8 if args.view < 0 else args.view        # the arm's view mix, one view per step
+        s, st, n_sampled, wall = cpu_oracle_view_seconds(args.cpu_tokens, threads, view=view)
         if i >= args.warmup:
             secs.append(s)
+            walls.append(wall)
             info = (st, n_sampled)
         if time.perf_counter() - t_start > 240 and secs:
             break
     value = len(secs) / sum(secs)
     st, n_sampled = info
+    sample = ("1 view per step (views cycle over the 8-view circle) through the CPU oracle = torch fp32 restatement of the "
+              "reference modules + C splat oracle (the reference itself needs PyTorch3D CUDA ops and hard-coded .cuda()), "
+              "%d host threads; every stage measured in full except the sampler: %d tokens per step timed reference-style "
+              "(one full forward per token, %.3f s/token) and scaled to the view's sampled cells (last view: %d). "
+              "value = 1 / extrapolated seconds per view; ms_per_step = measured wall per step (%.0f%% of a view's "
+              "extrapolated cost was actually executed)"
+              % (threads, args.cpu_tokens, st["lmconv_per_token"], n_sampled, 100.0 * sum(walls) / sum(secs)))
+    cfg = workload_config(args, world)
+    cfg["reference_sample"] = "1 view per step, sampler extrapolated from %d tokens" % args.cpu_tokens
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs),
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "1 view per step through the CPU oracle (torch fp32 restatement of the reference modules + "
-                                   "C splat oracle; the reference itself needs PyTorch3D CUDA ops and hard-coded .cuda()); "
-                                   "sampler timed reference-style on %d tokens (%.3f s/token) and extrapolated to the view's %d "
-                                   "sampled cells" % (args.cpu_tokens, st["lmconv_per_token"], n_sampled),
-                         "stage_seconds": st},
+        "impl": "reference", "metric": METRIC, "value": value, "value_kind": "extrapolated from a bounded sample (see cpu_baseline.sample)",
+        "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs),
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "extrapolated_ms_per_view": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "stage_seconds": st},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def run_supervised():
-    """Single-GPU runs measure in a child process and re-measure (at most twice) when the child dies: a CUDA fault
-    (the intermittent "unspecified launch failure" seen at batch 128) kills the CUDA
-    context, so it cannot be retried in-process.  The JSON line reports how many attempts it took (`attempts`)."""
-    rc = 1
-    batch_given = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
-    for attempt in (1, 2, 3):
-        # last resort when the batch was left at its default: half of it
-        extra = ["--batch", "32"] if attempt == 3 and not batch_given else []
-        p = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + extra,
-                           env=dict(os.environ, PS_BENCH_CHILD="1"), stdout=subprocess.PIPE, text=True)
-        rc = p.returncode
-        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
-        if rc == 0 and lines:
-            line = json.loads(lines[-1])
-            line["attempts"] = attempt
-            if extra:
-                line["config"]["fallback"] = "two runs at the default batch died; measured at batch 32 per GPU"
-            print(json.dumps(line), flush=True)
-            return 0
-        sys.stderr.write("bench.py: attempt %d failed (exit code %d)%s\n" % (attempt, rc, ", measuring again" if attempt < 3 else ""))
-    raise SystemExit(rc if rc else 1)
-
-
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
-
-    if os.environ.get("PS_BENCH_CHILD") != "1" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        return run_supervised()
 
     import torch
     import torch.distributed as dist
@@ -285,6 +279,8 @@ def main():
         import datetime
         # a rank that dies must not leave the others in a collective for NCCL's default 10 minutes
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=3))
+        # one process per GPU share the host: the native order / mask / level code gets cores / world worker threads
+        os.environ.setdefault("PS_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
 
     from pixelsynth_b200 import _lib
     from pixelsynth_b200.models.base_model import BaseModel
@@ -295,10 +291,15 @@ def main():
     B = args.batch
     opt = make_opt()
     model = ZbufferModelPts(opt, device=dev)
-    host_batch = make_batch(B, rank % 8)
+    host_batch = make_batch(B, batch_views(args, rank))
 
-    # ---- job start: the source images live on rank 0 and are broadcast once over NCCL ----
+    # ---- job start: the source images live on rank 0 and are broadcast once over NCCL.  The communicator
+    # is created by a warm-up collective first, so `broadcast_ms` is the transfer, not NCCL's initialisation ----
     src = host_batch["images"][0].to(dev) if rank == 0 else torch.empty((B, 3, W, W), device=dev)
+    if world > 1:
+        warm = torch.zeros(1, device=dev)
+        dist.broadcast(warm, 0)
+        torch.cuda.synchronize()
     bcast_ms = broadcast_sources(src, world)
     dev_batch = {"images": [src, src],
                  "cameras": [{k: v.to(dev) for k, v in c.items()} for c in host_batch["cameras"]]}
@@ -326,17 +327,21 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        _lib.check_wedge("bench.py")          # a wedged kernel's numbers are not numbers
         launches = L.ps_launch_count()
+        per_rank = [ms]
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches
+            t = torch.zeros(world, device=dev)
+            t[rank] = ms
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank = [float(x) for x in t.tolist()]
+            ms = max(per_rank)
+        return ms, launches, per_rank
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res, launches = timed(step_resident, args.steps, args.warmup)
+    ms_res, launches, ms_res_ranks = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e through the reference-facing wrapper with host buffers ----
@@ -353,7 +358,7 @@ def main():
         h_out.copy_(img, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
     h2d = sum(t.numel() * 4 for t in pinned["images"]) + sum(v.numel() * 4 for c in pinned["cameras"] for v in c.values())
     d2h = h_out.numel() * 4
 
@@ -387,10 +392,57 @@ def main():
     L.ps_timing_enable(0)
     maps_ms = _lib.kernel_time_ms("fine_kernel")[0] / 5
     _lib.kernel_time_ms(None)
+    # the same launch on SURVEY 8d's own distribution: depth ~ U[min_z, max_z] (seed 0) instead of the U-Net's output
+    depth_u = (torch.rand(nb, 1, W, W, generator=torch.Generator().manual_seed(0)) * 9.5 + 0.5).to(dev)
+    run_maps_u = lambda: torch.ops.pixelsynth_b200.splat(depth_u, feat16, mats, W, W, K_PP, RADIUS, 1.0, 2, 0, 13, 1e-2, True, False)
+    for _ in range(3):
+        run_maps_u()
+    torch.cuda.synchronize()
+    L.ps_timing_enable(1)
+    for _ in range(5):
+        run_maps_u()
+    torch.cuda.synchronize()
+    L.ps_timing_enable(0)
+    maps_u_ms = _lib.kernel_time_ms("fine_kernel")[0] / 5
+    _lib.kernel_time_ms(None)
     cells_processed = int(model.outpaint2.last_levels[-1])   # rows the sampler pushed through the network this step
     levels = len(model.outpaint2.last_levels) - 1
     cells_sampled = int(last["sample_mask"].sum())
     levels_prefix = int(model.outpaint2.last_first_b)
+
+    # ---- BASELINE configs[2]: batch 32, right half of the 32x32 code grid masked (512 cells / image), T = 0.7,
+    # uniforms seed 1.  tokens/s = 32 * 512 / device time of the sampler launch (prefix included; order /
+    # mask / level construction on the host excluded and reported) ----
+    import numpy as np
+    from pixelsynth_b200 import lmconv as lm
+    bg3 = torch.zeros(32, W, W, dtype=torch.bool)
+    bg3[:, :, W // 2:] = True
+    t0 = time.perf_counter()
+    _, order3, words3, smask3 = lm.glue_host(bg3)
+    prep3 = model.outpaint2.prepare(order3, words3, smask3, 0)
+    host3_ms = 1e3 * (time.perf_counter() - t0)
+    codes3 = torch.randint(0, 512, (32, 32, 32), generator=torch.Generator().manual_seed(0)).to(dev)
+    uni3 = torch.rand(32, 1024, generator=torch.Generator().manual_seed(1)).to(dev)
+    for _ in range(3):
+        model.outpaint2.sample(codes3, order3, words3, smask3, uni3, 0.7, prepared=prep3)
+    torch.cuda.synchronize()
+    L.ps_timing_enable(1)
+    for _ in range(5):
+        model.outpaint2.sample(codes3, order3, words3, smask3, uni3, 0.7, prepared=prep3)
+    torch.cuda.synchronize()
+    L.ps_timing_enable(0)
+    c3_ms = _lib.kernel_time_ms("lmconv_tc_kernel")[0] / 5
+    _lib.kernel_time_ms(None)
+    c3_cells, c3_levels, c3_first_b = int(prep3["offs"][-1]), len(prep3["offs"]) - 1, int(prep3["first_b"])
+    _lib.check_wedge("bench.py")
+
+    # whole-job sampler counts: every rank's cells (ranks carry different images)
+    counts = [cells_sampled, cells_processed]
+    if world > 1:
+        t = torch.tensor(counts, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        counts = [int(x) for x in t.tolist()]
+    job_cells_sampled, job_cells_processed = counts
 
     if rank != 0:
         if world > 1:
@@ -417,7 +469,17 @@ def main():
         "splat fine_kernel (maps emitted)": {
             "bound": "hbm", "achieved": BYTES_PER_VIEW_SPLAT_MAPS * nb / (maps_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "ms_per_step": maps_ms, "views_per_launch": nb,
-            "note": "not part of the timed step: the map-emitting parity configuration, measured in this run"},
+            "note": "not part of the timed step: the map-emitting parity configuration on the U-Net's depth, measured in this run"},
+        "splat fine_kernel (maps emitted, uniform depth)": {
+            "bound": "hbm", "achieved": BYTES_PER_VIEW_SPLAT_MAPS * nb / (maps_u_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "ms_per_step": maps_u_ms, "views_per_launch": nb,
+            "note": "same launch on SURVEY 8d's distribution: depth ~ U[0.5, 10], seed 0"},
+        "lmconv_tc_kernel (config 3)": {
+            "bound": "tensor", "achieved": FLOP_PER_CELL * c3_cells / (c3_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+            "ms_per_step": c3_ms, "tokens_per_s": 32 * 512 / (c3_ms * 1e-3), "cells_processed": c3_cells,
+            "cells_sampled": 32 * 512, "dependency_levels": c3_levels, "prefix_levels": c3_first_b,
+            "host_order_masks_levels_ms": host3_ms,
+            "note": "BASELINE configs[2]: batch 32, right half of the code grid masked, T 0.7; not part of the timed step"},
         "conv_igemm_kernel": {"bound": "tensor", "achieved": conv_flops / (per_step["conv_igemm_kernel"][0] * 1e-3) / 1e12,
                               "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": per_step["conv_igemm_kernel"][0],
                               "launches_per_step": per_step["conv_igemm_kernel"][1]},
@@ -429,8 +491,8 @@ def main():
         pass
     for k, v in rl.items():
         v["frac"] = v["achieved"] / v["peak"]
-        v["share_of_step"] = 0.0 if "maps" in k else v["ms_per_step"] / step_ms
-    dom = max((k for k in rl if "maps" not in k), key=lambda k: rl[k]["ms_per_step"])
+        v["share_of_step"] = 0.0 if ("maps" in k or "config 3" in k) else v["ms_per_step"] / step_ms
+    dom = max((k for k in rl if "maps" not in k and "config 3" not in k), key=lambda k: rl[k]["ms_per_step"])
     roof = dict(rl[dom])
     roof.update({"kernel": dom, "traffic": traffic.get(dom), "traffic_source": traffic.get("source"), "peak_source": peak_src})
     views_per_step = B * world
@@ -441,16 +503,21 @@ def main():
         "e2e": {"value": views_per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "ZbufferModelPts.forward + BaseModel rescale, host pinned in/out"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rl,
-        "lmconv_tokens_per_s": cells_sampled * world / (per_step["lmconv_tc_kernel"][0] * 1e-3),
-        "lmconv_cells_per_s": cells_processed * world / (per_step["lmconv_tc_kernel"][0] * 1e-3),
+        "lmconv_tokens_per_s": job_cells_sampled / (per_step["lmconv_tc_kernel"][0] * 1e-3),
+        "lmconv_cells_per_s": job_cells_processed / (per_step["lmconv_tc_kernel"][0] * 1e-3),
+        "lmconv_config3_tokens_per_s": 32 * 512 / (c3_ms * 1e-3),
+        "ms_per_step_per_rank": [m / args.steps for m in ms_res_ranks],
         "broadcast_ms": bcast_ms,
     }
     if world == 1 and not args.no_cpu_baseline:
-        s, st, n_sampled = cpu_oracle_view_seconds(args.cpu_tokens, 1)
-        line["cpu_baseline"] = {"value": 1.0 / s, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "1 view through the CPU oracle, one thread; sampler timed reference-style on %d tokens "
-                                          "(%.3f s/token) and extrapolated to the view's %d sampled cells" %
-                                          (args.cpu_tokens, st["lmconv_per_token"], n_sampled),
+        cores = os.cpu_count() or 1
+        v0 = 0 if args.view < 0 else args.view
+        s, st, n_sampled, wall = cpu_oracle_view_seconds(args.cpu_tokens, cores, view=v0)
+        line["cpu_baseline"] = {"value": 1.0 / s, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "1 view (circle view %d) through the CPU oracle on all %d host threads (%.1f s of CPU "
+                                          "wall); sampler timed reference-style on %d tokens (%.3f s/token) and extrapolated "
+                                          "to the view's %d sampled cells" %
+                                          (v0, cores, wall, args.cpu_tokens, st["lmconv_per_token"], n_sampled),
                                 "stage_seconds": st}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -283,6 +283,15 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
  * buffer of 8 x 1024 int64 (NULL switches it off).  Not part of the product path. */
 void ps_lmconv_tc_set_trace(void* dev_buffer);
 
+/* Watchdog of the tensor-core kernels.  Their barrier waits give up after ~1 s (a wedged producer/consumer protocol is
+ * a bug, never a legitimate wait), record where in pinned host memory and let the kernel run to completion on garbage
+ * instead of hanging the device.  The record is sticky: from then on ps_conv_igemm and ps_lmconv_tc_run fail with
+ * PS_ECUDA before launching anything, and ps_wedge_poll returns 1 (info8: [1] block, [2] thread, [3] shared address
+ * of the mbarrier or 0xffffffff for a progress-word wait, [4] parity / needed progress), without any device
+ * synchronisation.  Callers that hand results to someone else poll after their own synchronisation. */
+int ps_wedge_poll(unsigned int* info8_or_null);
+void ps_wedge_reset(void);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels  are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;
  * ps_timing_collect(NULL, ...) returns the sum over all names and releases the events. */

@@ -40,6 +40,8 @@ SIGNATURES = {
     "ps_lmconv_levels_host": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p]),
     "ps_lmconv_tc_run": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_f, c_p, c_p, c_sz, c_p]),
     "ps_lmconv_tc_set_trace": (None, [c_p]),
+    "ps_wedge_poll": (c_i, [c_p]),
+    "ps_wedge_reset": (None, []),
     "ps_launch_count": (ctypes.c_longlong, []),
     "ps_launch_count_reset": (None, []),
     "ps_timing_enable": (None, [c_i]),
@@ -76,6 +78,17 @@ def check(rc, what):
         L = lib()
         raise PixelSynthB200Error(
             f"{what}: {L.ps_error_string(rc).decode()} ({rc}): {L.ps_last_error_detail().decode()}")
+
+
+def check_wedge(what="pixelsynth_b200"):
+    """Raises if any tensor-core kernel launched so far gave up on a barrier wait (its output is garbage).  Host-memory
+    read, no device synchronisation; call it after the synchronisation that hands results to the caller."""
+    info = (ctypes.c_uint * 8)()
+    if lib().ps_wedge_poll(info):
+        raise PixelSynthB200Error(
+            f"{what}: a kernel wedged its barrier protocol (block {info[1]}, thread {info[2]}, "
+            f"{'progress wait' if info[3] == 0xffffffff else 'mbarrier at shared 0x%x' % info[3]}, value {info[4]}); "
+            "results since then are garbage")
 
 
 def ptr(t):

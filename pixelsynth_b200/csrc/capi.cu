@@ -1,6 +1,7 @@
 // Library-wide C-ABI bookkeeping: version, error strings, launch counter.
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -21,6 +22,31 @@ void timing_begin(const char* name, cudaStream_t stream) {
   if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
   cudaEventRecord(t.a, stream);
   g_timed.push_back(t);
+}
+
+unsigned int* wedge_host_words() {
+  static unsigned int* words = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!words) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 8 * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    memset(p, 0, 8 * sizeof(unsigned int));
+    words = (unsigned int*)p;
+  }
+  return words;
+}
+
+int wedge_check(const char* func) {
+  unsigned int* w = wedge_host_words();
+  if (w && *(volatile unsigned int*)w) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "block %u thread %u %s 0x%x value %u", w[1], w[2],
+             w[3] == 0xffffffffu ? "progress wait, needed" : "mbarrier at shared", w[3] == 0xffffffffu ? w[4] : w[3], w[4]);
+    return fail(PS_ECUDA, "%s: an earlier launch wedged its barrier protocol and its results are garbage (%s); ps_wedge_reset() clears this",
+                func, buf);
+  }
+  return PS_OK;
 }
 
 void timing_end(cudaStream_t stream) {
@@ -47,6 +73,18 @@ const char* ps_last_error_detail(void) { return ps::g_err_detail; }
 
 long long ps_launch_count(void) { return ps::g_launches; }
 void ps_launch_count_reset(void) { ps::g_launches = 0; }
+
+int ps_wedge_poll(unsigned int* info8) {
+  unsigned int* w = ps::wedge_host_words();
+  if (!w) return 0;
+  if (info8) memcpy(info8, w, 8 * sizeof(unsigned int));
+  return *(volatile unsigned int*)w != 0;
+}
+
+void ps_wedge_reset(void) {
+  unsigned int* w = ps::wedge_host_words();
+  if (w) memset(w, 0, 8 * sizeof(unsigned int));
+}
 
 void ps_timing_enable(int on) { ps::g_timing_on = on; }
 

@@ -52,6 +52,30 @@ void timing_end(cudaStream_t stream);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Wedge watchdog of the tensor-core kernels (tc05.cuh): 8 pinned, mapped host words shared by every device; word 0 != 0
+// once any barrier wait of any launch timed out (sticky until ps_wedge_reset).  wedge_check() is the first thing every
+// C-ABI entry point that launches such a kernel does.
+unsigned int* wedge_host_words();
+int wedge_check(const char* func);
+// called by a translation unit before it launches: points its copy of g_wedge_host at the host words and clears its
+// device-side flag, once per (host thread, device)
+#define PS_WEDGE_ARM()                                                                                \
+  do {                                                                                                \
+    static thread_local int armed_dev__ = -1;                                                         \
+    int dev__ = 0;                                                                                    \
+    PS_CUDA(cudaGetDevice(&dev__));                                                                   \
+    if (armed_dev__ != dev__) {                                                                       \
+      unsigned int* h__ = ps::wedge_host_words();                                                     \
+      if (!h__) return ps::fail(PS_ECUDA, "%s: cannot allocate the pinned watchdog words%s", __func__); \
+      unsigned int* d__ = nullptr;                                                                    \
+      PS_CUDA(cudaHostGetDevicePointer((void**)&d__, h__, 0));                                        \
+      unsigned int zero__[8] = {0};                                                                   \
+      PS_CUDA(cudaMemcpyToSymbol(g_wedge_host, &d__, sizeof(d__)));                                   \
+      PS_CUDA(cudaMemcpyToSymbol(g_wedge, zero__, sizeof(zero__)));                                   \
+      armed_dev__ = dev__;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
 // bump allocator over the caller's workspace
 struct Workspace {
   char* base;

@@ -636,6 +636,8 @@ using namespace ps;
 
 extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   PS_CHECK_ARG(d != nullptr);
+  if (int rcw = wedge_check(__func__)) return rcw;
+  PS_WEDGE_ARM();
   PS_CHECK_ARG(d->in[0].ptr && d->weights);
   PS_CHECK_ARG(d->N >= 1 && d->Hout >= 1 && d->Wout >= 1 && d->Cout >= 1);
   PS_CHECK_ARG(d->stride == 1 || d->stride == 2);

@@ -197,7 +197,10 @@ __global__ void embed_kernel(const long long* __restrict__ ids, int total, int D
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total * D) return;
   const int p = idx / D, d = idx - p * D;
-  out[idx] = __float2bfloat16(embed[(size_t)d * J + (int)ids[p]]);
+  // an id outside the codebook (a caller's bug) must not index outside `embed`: it reads code 0 .. J-1 by clamping
+  const long long id = ids[p];
+  const int j = id < 0 ? 0 : (id >= J ? J - 1 : (int)id);
+  out[idx] = __float2bfloat16(embed[(size_t)d * J + j]);
 }
 
 // get_combined: a * (1 - bg) + b * bg per pixel, NCHW f32, bg (N,H,W) u8

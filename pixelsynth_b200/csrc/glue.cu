@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <queue>
 #include <tuple>
+#include <stdlib.h>
+
 #include <thread>
 #include <vector>
 
@@ -159,13 +161,21 @@ extern "C" int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, in
     }
   };
   unsigned hw = std::thread::hardware_concurrency();
+  if (const char* e = getenv("PS_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));  // one process per GPU: cores / world
   int nth = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
   nth = std::min(nth, B / 2);  // at least two images per thread
   if (nth <= 1) {
     work(0, B);
   } else {
     std::vector<std::thread> th;
-    for (int t = 0; t < nth; ++t) th.emplace_back(work, (int)((long long)B * t / nth), (int)((long long)B * (t + 1) / nth));
+    for (int t = 0; t < nth; ++t) {
+      const int lo = (int)((long long)B * t / nth), hi = (int)((long long)B * (t + 1) / nth);
+      try {
+        th.emplace_back(work, lo, hi);
+      } catch (...) {  // thread creation failed: std::system_error must not cross the C ABI, do the share inline
+        work(lo, hi);
+      }
+    }
     for (auto& x : th) x.join();
   }
   return PS_OK;

@@ -138,7 +138,8 @@ struct TcParams {
 
 struct TcSmem {
   uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[3], cfull;
-  uint32_t tmem_slot, step_count;
+  uint32_t tmem_slot, pad_steps;
+  uint32_t warp_steps[4];  // finished cache tensors per epilogue warp (the tile's progress is their minimum)
   Tile tile;
   int tile_index, pad_;
   ps_lmconv_row rows[128];
@@ -240,13 +241,7 @@ __device__ __noinline__ unsigned int wait_progress(const unsigned int* prog, int
     if ((spins & 63u) == 63u) {
       if (*(volatile unsigned int*)&g_wedge[0]) return 0xffffffffu;
       if (clock64() - t0 > 2000000000ll) {
-        if (lane == 0 && atomicCAS(&g_wedge[0], 0u, 1u) == 0u) {
-          g_wedge[1] = blockIdx.x;
-          g_wedge[2] = threadIdx.x;
-          g_wedge[3] = 0xffffffffu;
-          g_wedge[4] = need;
-          __threadfence();
-        }
+        if (lane == 0) wedge_report(0xffffffffu, need);
         return 0xffffffffu;
       }
     }
@@ -277,7 +272,7 @@ struct Epi {
   // the cache rows of one more tensor have been written by this warp
   __device__ __forceinline__ void step_done() const {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) red_release_cta_shared_inc(&sm->step_count);
+    if ((threadIdx.x & 31) == 0) red_release_cta_shared_inc(&sm->warp_steps[(threadIdx.x >> 5) & 3]);
   }
   // One 16-channel piece j (channels 16j..16j+15) of a finished tensor: cache write + centre operand of the next GEMM.
   __device__ __forceinline__ void emit16(int form, int j, const float* x, int tensor, bool raw) const {
@@ -332,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     const int t = (int)atomicAdd(p.sync, 1u);
     sm.tile_index = t;
     sm.tile = p.tiles[t];
-    sm.step_count = 0;
+    sm.warp_steps[0] = sm.warp_steps[1] = sm.warp_steps[2] = sm.warp_steps[3] = 0;
   }
   for (int i = tid; i < p.n_total; i += TC_THREADS) sm.sched[i] = pack_chunk(p.chunks[i]);
   __syncthreads();
@@ -457,13 +452,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       }
     }
   } else if (warp == 10) {
-    // ===== progress publisher: the epilogue warps count finished cache tensors in shared memory; this warp makes
+    // ===== progress publisher: every epilogue warp counts its finished cache tensors in shared memory; this warp makes
     // them visible device-wide (the fence is cumulative over what it observed) and moves the tile's progress word =====
     if (lane == 0) {
       unsigned int* mine = p.sync + 16 + tile_index;
       unsigned int published = 0;
       while (published < PROG_DONE) {
-        const unsigned int done = ld_acquire_cta_shared(&sm.step_count) >> 2;  // four epilogue warps per step
+        // the slowest epilogue warp's count (a sum over the warps would overstate it when one warp lags)
+        const unsigned int done =
+            min(min(ld_acquire_cta_shared(&sm.warp_steps[0]), ld_acquire_cta_shared(&sm.warp_steps[1])),
+                min(ld_acquire_cta_shared(&sm.warp_steps[2]), ld_acquire_cta_shared(&sm.warp_steps[3])));
         if (done > published) {
           __threadfence();
           st_release_gpu(mine, done);
@@ -502,10 +500,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     if (verified < (unsigned int)tile.wait_start)
       verified = wait_progress(prog, tile.prev_first, tile.prev_count, (unsigned int)tile.wait_start);
     for (int i = 0; i < nchunks; ++i) {
+      const int st = (i >> 1) % nst;
+      // EVERY gather warp waits for EVERY use of every ring stage, in ring order, whether or not it fills a chunk there.
+      // A parity wait is only unambiguous for a waiter that is at most one phase behind the barrier.  A warp that
+      // only waited where it owned a chunk could jump 7 chunks ahead (its next chunk lies behind a GEMM's three
+      // centre-tap chunks), i.e. 4 stage uses, on a 3-stage ring (128-row tiles): with the MMA warp parked on the
+      // epilogue's operand the `empty` barrier was then still TWO phases back, the parity test passed, the warp
+      // overwrote a stage that had not been multiplied yet and its 32 arrivals landed in the wrong phase of `full`
+      // -- wrong activations, and sooner or later an mbarrier arrival overflow = "unspecified launch failure"
+      // (round 1's intermittent fault at batch 128; profiles/r02_launch_failure_rootcause.txt).
+      if (!(i & 1)) mbar_wait(&sm.empty[st], ((uint32_t)((i >> 1) / nst) & 1u) ^ 1u);
       const Chunk ch = unpack_chunk(sm.sched[i]);
       if (ch.a_kind != A_GATHER && ch.a_kind != A_CENTRE) continue;
       if ((seen++ & 3) != gw) continue;
-      const int st = (i >> 1) % nst;
       const int kg = ch.kc * 8 + g;
       int bitpos, off;  // mask bit to test, byte offset from the row's base
       if (ch.a_kind == A_GATHER) {
@@ -524,7 +531,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         bitpos = kg < ch.cin8 ? 27 : 31;
         off = ch.a_tensor * LMT_CELLS * (LMT_ACT * 2) + (ch.ch_off8 + kg) * 16;
       }
-      mbar_wait(&sm.empty[st], ((uint32_t)((i >> 1) / nst) & 1u) ^ 1u);
       if (lane == 0) TC_TRACE(1, i);
       const uint32_t soff = st * stage_bytes + (i & 1) * slot_bytes;
       if (!(p.debug & 2)) {
@@ -820,13 +826,20 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
   if (const char* e = getenv("PS_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));  // tests pin the worker count
   const int T = std::max(1, std::min({(int)(hw ? hw : 1), 32, B / 4}));
   std::vector<int> tops_a(T, -1), tops_b(T, -1), bad(T, 0);
+  // worker c runs fn(c); a thread that cannot be created (std::system_error must not cross the C ABI) is run inline
   auto run_workers = [&](auto&& fn) {
     if (T == 1) {
       fn(0);
       return;
     }
     std::vector<std::thread> th;
-    for (int c = 0; c < T; ++c) th.emplace_back(fn, c);
+    for (int c = 0; c < T; ++c) {
+      try {
+        th.emplace_back(fn, c);
+      } catch (...) {
+        fn(c);
+      }
+    }
     for (auto& t : th) t.join();
   };
   auto image_range = [&](int c, int& lo, int& hi) {
@@ -842,8 +855,9 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
       const int* ord = order + (size_t)b * LMT_CELLS;
       const uint16_t* w = words + (size_t)b * 3 * LMT_CELLS;
       int* lv = level.data() + (size_t)b * LMT_CELLS;
+      std::fill(rank.begin(), rank.end(), -1);
       for (int i = 0; i < LMT_CELLS; ++i) {
-        if (ord[i] < 0 || ord[i] >= LMT_CELLS) {
+        if (ord[i] < 0 || ord[i] >= LMT_CELLS || rank[ord[i]] != -1) {  // out of range, or a cell listed twice
           bad[c] = 1;
           break;
         }
@@ -956,6 +970,8 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
 int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* rows_dev, const int* level_offsets_host,
                      int n_levels, int first_b_level, long long* codes, const float* uniforms, int uniforms_stride,
                      float temperature, float* logits_out, void* cache, size_t cache_bytes, void* stream) {
+  if (int rcw = wedge_check(__func__)) return rcw;
+  PS_WEDGE_ARM();
   PS_CHECK_ARG(plan && plan->wblob && plan->chunks && plan->w_uinit && plan->bias && codes && cache);
   PS_CHECK_ARG(B >= 0 && n_levels >= 0 && temperature > 0.0f);
   PS_CHECK_ARG(plan->n_chunks_body > 0 && plan->n_chunks_total >= plan->n_chunks_body);
@@ -995,6 +1011,7 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // tiles in level order: a level's rows are split evenly over its tiles
   std::vector<Tile> tiles;
+  const int exp_bits = getenv("PS_TC_EXP") ? atoi(getenv("PS_TC_EXP")) : 0;  // developer aid: scheduling experiments
   int prev_first = 0, prev_count = 0;
   for (int l = 0; l < n_levels; ++l) {
     const int r0 = level_offsets_host[l], r1 = level_offsets_host[l + 1];
@@ -1006,6 +1023,9 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
     if (l >= first_b_level) {
       rpt = 32;
       while (rpt < 128 && (r1 - r0 + rpt - 1) / rpt > sms) rpt *= 2;
+      if (exp_bits & 2) rpt = 128;
+    } else if (exp_bits & 4) {
+      rpt = 32;
     }
     const int nt = (r1 - r0 + rpt - 1) / rpt;
     const int first = (int)tiles.size();
@@ -1018,6 +1038,7 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
       tl.prev_count = prev_count;
       // first B level: the whole prefix must be cached; later B levels: the previous level's tokens must be drawn
       tl.wait_start = l < first_b_level ? 0 : (l == first_b_level ? LMT_TENSORS : PROG_DONE);
+      if (exp_bits & 1) tl.wait_start = PROG_DONE;  // no pipelining between prefix levels
       tiles.push_back(tl);
     }
     prev_first = first;
@@ -1029,13 +1050,27 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   char* tail = (char*)cache + align_up(tc_act_bytes(B), 256);
   Tile* tiles_dev = (Tile*)tail;
   unsigned int* sync_dev = (unsigned int*)(tail + align_up(tc_max_tiles(B) * sizeof(Tile), 256));
-  PS_CUDA(cudaMemcpyAsync(tiles_dev, tiles.data(), (size_t)n_tiles * sizeof(Tile), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  // `tiles` is pageable host memory that dies with this call, and the sampler below is the one kernel of the path that
-  // was seen to fault intermittently (batch 128 only, never under CUDA_LAUNCH_BLOCKING / compute-sanitizer; DESIGN.md
-  // section 8).  Until that is understood the launch is serialised: wait for the uploads (the table is ~44 KB at batch
-  // 128, so by the documented rules the driver has staged it already -- this removes the doubt) and for everything
-  // queued before them, which the sampler would wait for anyway.
-  PS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  // The tile table is staged in a pinned buffer that outlives the call (one per host thread, grown on demand): the
+  // copy is asynchronous and nothing here waits for the stream.  A second call from the same thread reuses the buffer
+  // only after the previous call's copy has left it (event).
+  {
+    static thread_local Tile* pin = nullptr;
+    static thread_local size_t pin_cap = 0;
+    static thread_local cudaEvent_t pin_evt = nullptr;
+    if (pin_evt) PS_CUDA(cudaEventSynchronize(pin_evt));
+    if (pin_cap < (size_t)n_tiles) {
+      if (pin) cudaFreeHost(pin);
+      pin = nullptr;
+      pin_cap = 0;
+      const size_t cap = std::max<size_t>(4096, (size_t)n_tiles * 2);
+      PS_CUDA(cudaHostAlloc((void**)&pin, cap * sizeof(Tile), cudaHostAllocDefault));
+      pin_cap = cap;
+    }
+    if (!pin_evt) PS_CUDA(cudaEventCreateWithFlags(&pin_evt, cudaEventDisableTiming));
+    memcpy(pin, tiles.data(), (size_t)n_tiles * sizeof(Tile));
+    PS_CUDA(cudaMemcpyAsync(tiles_dev, pin, (size_t)n_tiles * sizeof(Tile), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    PS_CUDA(cudaEventRecord(pin_evt, (cudaStream_t)stream));
+  }
   PS_CUDA(cudaMemsetAsync(sync_dev, 0, ((size_t)n_tiles + 16) * sizeof(unsigned int), (cudaStream_t)stream));
   p.tiles = tiles_dev;
   p.n_tiles = n_tiles;
@@ -1052,16 +1087,6 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   lmconv_tc_kernel<<<n_tiles, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
   PS_LAUNCHED();
   PS_TIME_END((cudaStream_t)stream);
-  if (getenv("PS_CHECK_WEDGE")) {  // developer aid: synchronise and report a wedged barrier protocol
-    unsigned int w[8] = {0};
-    PS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    PS_CUDA(cudaMemcpyFromSymbol(w, g_wedge, sizeof(w)));
-    if (w[0]) {
-      char buf[160];
-      snprintf(buf, sizeof(buf), "block %u thread %u barrier smem 0x%x parity %u", w[1], w[2], w[3], w[4]);
-      return fail(PS_ECUDA, "%s: barrier protocol wedged: %s", __func__, buf);
-    }
-  }
   return PS_OK;
 }
 

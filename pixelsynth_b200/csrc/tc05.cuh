@@ -19,9 +19,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Blocks until the phase with the given parity has completed.  A wait longer than ~1 s means the kernel's barrier
-// protocol is wedged (a bug): the first such wait records who / where in g_wedge and every wait then falls through,
-// so the kernel terminates (with garbage) instead of hanging the device; the host checks g_wedge after the launch.
+// protocol is wedged (a bug).  The first such wait records who / where in g_wedge AND in the library's pinned, mapped
+// host words (g_wedge_host, armed by ps::wedge_arm before every launch of a kernel that uses these waits), and every
+// later wait falls through so the kernel terminates instead of hanging the device.  The host words are sticky: every
+// C-ABI entry point checks them first and fails with PS_ECUDA from then on (ps_wedge_poll / ps_wedge_reset), so a
+// wedged launch can never pass for a result.
 static __device__ unsigned int g_wedge[8];
+static __device__ unsigned int* g_wedge_host;
+
+static __device__ __noinline__ void wedge_report(unsigned int where, unsigned int what) {
+  if (atomicCAS(&g_wedge[0], 0u, 1u) == 0u) {
+    g_wedge[1] = blockIdx.x;
+    g_wedge[2] = threadIdx.x;
+    g_wedge[3] = where;
+    g_wedge[4] = what;
+    volatile unsigned int* h = g_wedge_host;
+    if (h) {
+      h[1] = blockIdx.x;
+      h[2] = threadIdx.x;
+      h[3] = where;
+      h[4] = what;
+      __threadfence_system();
+      h[0] = 1u;
+    }
+    __threadfence_system();
+  }
+}
 
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -46,13 +69,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
     if ((spins & 63) == 63) {
       if (*(volatile unsigned int*)&g_wedge[0]) return;
       if (clock64() - t0 > 2000000000ll) {
-        if (atomicCAS(&g_wedge[0], 0u, 1u) == 0u) {
-          g_wedge[1] = blockIdx.x;
-          g_wedge[2] = threadIdx.x;
-          g_wedge[3] = smem_u32(bar);
-          g_wedge[4] = parity;
-          __threadfence();
-        }
+        wedge_report(smem_u32(bar), parity);
         return;
       }
     }

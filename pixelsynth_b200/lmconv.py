@@ -200,7 +200,7 @@ class LmconvB200:
         self.plan.wblob, self.plan.chunks = self.wblob.data_ptr(), self.chunks.data_ptr()
         self.plan.w_uinit, self.plan.bias = self.w_uinit.data_ptr(), self.bias.data_ptr()
         self._cache = None
-        self._rows_pin = self._rows_dev = self._rows_evt = None
+        self._rows_pin = self._rows_evt = None
         self.last_levels = None
 
     @staticmethod
@@ -237,20 +237,25 @@ class LmconvB200:
             n = rows.shape[0]
             if self._rows_pin is None or self._rows_pin.shape[0] < n:
                 self._rows_pin = torch.empty((max(n, 1024), 16), dtype=torch.uint8).pin_memory()
-                self._rows_dev = torch.empty((self._rows_pin.shape[0], 16), dtype=torch.uint8, device=self.device)
             if self._rows_evt is not None:
                 self._rows_evt.synchronize()      # the previous upload has left the staging buffer
             self._rows_pin[:n].numpy()[:] = rows
-            rows_d = self._rows_dev[:n]
+            # every prepare() owns its device rows: two prepared calls can be in flight without sharing a buffer
+            rows_d = torch.empty((n, 16), dtype=torch.uint8, device=self.device)
             rows_d.copy_(self._rows_pin[:n], non_blocking=True)
             self._rows_evt = torch.cuda.Event()
             self._rows_evt.record()
-        return dict(rows=rows_d, offs=offs, first_b=first_b, mode=mode)
+        # the kernel reads uniforms[b, k] for the k-th sampled cell of image b: the widest image sets the minimum width
+        need_u = 0 if smn is None else int(smn.reshape(smn.shape[0], -1).astype(bool).sum(1).max(initial=0))
+        return dict(rows=rows_d, offs=offs, first_b=first_b, mode=mode, need_uniforms=need_u,
+                    batch=int(np.asarray(ordn).reshape(-1, 1024).shape[0]))
 
     def _run(self, codes, prepared, uniforms, temperature):
         dev = self.device
         B = codes.shape[0]
         offs, first_b, mode, rows_d = prepared["offs"], prepared["first_b"], prepared["mode"], prepared["rows"]
+        if prepared.get("batch", B) != B:
+            raise ValueError(f"prepared levels are for {prepared['batch']} images, codes hold {B}")
         self.last_levels, self.last_first_b = offs, first_b
         codes_d = torch.as_tensor(codes).to(device=dev, dtype=torch.int64).reshape(B, 1024).clone()
         logits = torch.empty((B, 1024, 512), dtype=torch.float32, device=dev) if mode == 1 else None
@@ -260,6 +265,11 @@ class LmconvB200:
                 u = torch.as_tensor(uniforms)
                 # an asynchronous copy from pageable memory may read its source after the caller has dropped it
                 uni_d = u.to(device=dev, dtype=torch.float32, non_blocking=u.is_cuda or u.is_pinned()).reshape(B, -1).contiguous()
+                if uni_d.shape[1] < prepared.get("need_uniforms", 0):
+                    raise RuntimeError(f"uniforms: {uni_d.shape[1]} columns, but an image samples {prepared['need_uniforms']} "
+                                     "cells (one uniform number per sampled cell, in generation order)")
+            elif mode == 0:
+                raise RuntimeError("sampling needs the uniform numbers")
             nbytes = _lib.lib().ps_lmconv_tc_cache_bytes(B)
             if self._cache is None or self._cache.numel() < nbytes:
                 self._cache = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -269,11 +279,6 @@ class LmconvB200:
                     None if uni_d is None else uni_d.data_ptr(), 0 if uni_d is None else uni_d.shape[1], float(temperature),
                     None if logits is None else logits.data_ptr(), self._cache.data_ptr(), nbytes,
                     torch.cuda.current_stream().cuda_stream), "ps_lmconv_tc_run")
-                # The sampler runs alone: ps_lmconv_tc_run drains the stream before it launches, and the host waits here
-                # until the kernel is done (the GPU then idles for one launch latency).  An intermittent "unspecified
-                # launch failure" at batch 128 (profiles/r01_launch_failure_bisect.txt) never
-                # appeared when the sampler was serialised like this (CUDA_LAUNCH_BLOCKING run); its cause is open.
-                torch.cuda.current_stream().synchronize()
         return codes_d.view(B, 32, 32), logits
 
     def sample(self, codes, order, words, sample_mask, uniforms, temperature=1.0, prepared=None):

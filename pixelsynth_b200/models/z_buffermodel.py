@@ -83,7 +83,6 @@ class ZbufferModelPts(nn.Module):
         self.obs = [3, 32, 32]
         self.ranker = None
         self._bg_pin = None
-        self._prepared = None
 
     # -- z_buffermodel.py:120-184 ---------------------------------------------------------------
     def process_batch(self, batch):
@@ -150,14 +149,14 @@ class ZbufferModelPts(nn.Module):
         return torch.rand(B, 1024, generator=g)
 
     def get_best_sample(self, order, words, sample_mask, codes, background_mask, gen_fs, netD, input_img, noise=None,
-                        uniforms=None):
+                        uniforms=None, prepared=None):
         imgs = []
         n = int(_get(self.opt, "num_samples", 1) or 1)
         B = codes.shape[0]
         for i in range(n):
             u = uniforms if uniforms is not None else self._sampler_uniforms(i, B)
             sampled = self.outpaint2.sample(codes, order, words, sample_mask, u, float(_get(self.opt, "temperature", 1.0)),
-                                            prepared=getattr(self, "_prepared", None))
+                                            prepared=prepared)
             ar_sample = self.vqvae.decode_code(sampled)
             combined = self.get_combined(gen_fs, ar_sample, background_mask)
             imgs.append(self.projector.forward(combined, background_mask, noise))
@@ -205,9 +204,9 @@ class ZbufferModelPts(nn.Module):
             codes = self.vqvae.encode_top(gen_fs)
             ready.synchronize()
             _, order, words, sample_mask = self.get_masks_for_batch(output_RT, input_RTinv, self._bg_pin.numpy())
-            self._prepared = self.outpaint2.prepare(order, words, sample_mask, 0)
+            prepared = self.outpaint2.prepare(order, words, sample_mask, 0)   # passed explicitly: never reused by a later call
             gen_img = self.get_best_sample(order, words, sample_mask, codes, background_mask, gen_fs, netD, input_img,
-                                           noise, uniforms)
+                                           noise, uniforms, prepared=prepared)
             self.last = dict(depth=regressed_pts, gen_fs=gen_fs, background_mask=background_mask, order=order, words=words,
                              sample_mask=sample_mask, codes=codes, output_RT=output_RT)
         outputs = {"InputImg": input_img, "PredImg": gen_img, "PredDepthImg": regressed_pts / 5 - 1,
@@ -269,7 +268,6 @@ class ZbufferModelPts(nn.Module):
                     current_img, depth, K, K_inv, src_rt.contiguous(), src_inv.contiguous(), dst_rt.contiguous(),
                     dst_inv.contiguous(), cloud, feats, last_bg, last_out_inv)
                 _, order, words, sample_mask = self.get_masks_for_batch(dst_rt, src_inv, bg)
-                self._prepared = None
                 codes = self.vqvae.encode_top(gen_fs)
                 gen_img = self.get_best_sample(order, words, sample_mask, codes, bg, gen_fs, netD, input_img, noise, uniforms)
                 self.last_scene.append(dict(direction=direction, num=num, src=current_img, depth=depth, src_rt=src_rt,

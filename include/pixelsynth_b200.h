@@ -254,6 +254,16 @@ typedef struct {
   int b_uinit, b_nin;
   ps_lmconv_op ops[18];
   unsigned long long raw_mask;
+  /* The same schedule split in two for the sampled levels.  chain: the chunks whose operand is the row's own column
+   * (nin_skip, centre tap, nin_out) -- what a sampled cell's dependent chain really needs; the centre tap's first
+   * chunk does not accumulate.  halo: the gathered neighbour taps of GEMM g are chunks [halo_first[g], halo_first[g+1])
+   * of chunks_halo, their last chunk completes the accumulator; other CTAs turn them into per-row partial sums,
+   * part_col[g] = first of GEMM g's w_rows fp32 columns in a row of the partial-sum buffer (part_col[32] = row length). */
+  const ps_lmconv_chunk* chunks_chain; /* device */
+  int n_chain_body, n_chain_total;
+  const ps_lmconv_chunk* chunks_halo;  /* device */
+  int halo_first[33];
+  int part_col[33];
 } ps_lmconv_plan;
 
 /* device scratch ps_lmconv_tc_run needs for B images: activation cache + tile table + progress words */
@@ -290,6 +300,7 @@ void ps_lmconv_tc_set_trace(void* dev_buffer);
  * of the mbarrier or 0xffffffff for a progress-word wait, [4] parity / needed progress), without any device
  * synchronisation.  Callers that hand results to someone else poll after their own synchronisation. */
 int ps_wedge_poll(unsigned int* info8_or_null);
+int ps_wedge_log(unsigned int* out, int max_words); /* developer aid: raw watchdog words incl. the waiter snapshot */
 void ps_wedge_reset(void);
 
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels  are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)

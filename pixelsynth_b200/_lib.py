@@ -41,6 +41,7 @@ SIGNATURES = {
     "ps_lmconv_tc_run": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_f, c_p, c_p, c_sz, c_p]),
     "ps_lmconv_tc_set_trace": (None, [c_p]),
     "ps_wedge_poll": (c_i, [c_p]),
+    "ps_wedge_log": (c_i, [c_p, c_i]),
     "ps_wedge_reset": (None, []),
     "ps_launch_count": (ctypes.c_longlong, []),
     "ps_launch_count_reset": (None, []),

@@ -30,8 +30,8 @@ unsigned int* wedge_host_words() {
   std::lock_guard<std::mutex> lock(mu);
   if (!words) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, 8 * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
-    memset(p, 0, 8 * sizeof(unsigned int));
+    if (cudaHostAlloc(&p, ps::PS_WEDGE_WORDS * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    memset(p, 0, ps::PS_WEDGE_WORDS * sizeof(unsigned int));
     words = (unsigned int*)p;
   }
   return words;
@@ -81,9 +81,18 @@ int ps_wedge_poll(unsigned int* info8) {
   return *(volatile unsigned int*)w != 0;
 }
 
+/* developer aid: the snapshot of progress waiters taken when the watchdog tripped (8 words per waiter, see tc05.cuh) */
+int ps_wedge_log(unsigned int* out, int max_words) {
+  unsigned int* w = ps::wedge_host_words();
+  if (!w || !out) return 0;
+  const int n = max_words < ps::PS_WEDGE_WORDS ? max_words : ps::PS_WEDGE_WORDS;
+  memcpy(out, w, (size_t)n * sizeof(unsigned int));
+  return n;
+}
+
 void ps_wedge_reset(void) {
   unsigned int* w = ps::wedge_host_words();
-  if (w) memset(w, 0, 8 * sizeof(unsigned int));
+  if (w) memset(w, 0, ps::PS_WEDGE_WORDS * sizeof(unsigned int));
 }
 
 void ps_timing_enable(int on) { ps::g_timing_on = on; }

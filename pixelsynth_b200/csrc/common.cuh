@@ -55,6 +55,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Wedge watchdog of the tensor-core kernels (tc05.cuh): 8 pinned, mapped host words shared by every device; word 0 != 0
 // once any barrier wait of any launch timed out (sticky until ps_wedge_reset).  wedge_check() is the first thing every
 // C-ABI entry point that launches such a kernel does.
+constexpr int PS_WEDGE_WORDS = 8 + 256 * 8 + 64 * 4;  // the record + snapshots of up to 32 progress waiters and 32 mbarrier waiters
 unsigned int* wedge_host_words();
 int wedge_check(const char* func);
 // called by a translation unit before it launches: points its copy of g_wedge_host at the host words and clears its

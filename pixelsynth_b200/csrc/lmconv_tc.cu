@@ -65,7 +65,12 @@ constexpr int COL_OG = 320;      // TMEM columns [320, 400): the row's residual 
 constexpr int COL_A = 400;       // TMEM columns [400, 496): centre-tap A operand of the next GEMM (192 fp16 per row)
 constexpr int PROG_DONE = 34;    // progress word of a finished tile: 33 cache tensors + the sampled tokens
 constexpr int TC_NOPS = 18;
-constexpr int TC_MAX_CHUNKS = 728;
+constexpr int TC_MAX_CHUNKS = 724;
+constexpr int LMT_PART_COLS = 3680;    // fp32 partial-sum columns per row: 14 x 80 + 14 x 160 + 4 x 80 (one block per GEMM)
+constexpr int HALO_GROUP = 4;          // GEMMs per halo tile
+constexpr int CHAIN_ROWS = 32;         // rows of a chain tile
+constexpr int PART_ROW_BYTES = 640;    // one row's partial sums of one GEMM in shared memory (160 fp32)
+constexpr int PART_BUF_BYTES = CHAIN_ROWS * PART_ROW_BYTES;
 
 enum { A_GATHER = 0, A_CENTRE = 1, A_EPILOGUE = 2, A_TMEM = 3, A_REUSE = 4 };
 
@@ -103,8 +108,15 @@ enum { ROW_SAMPLED = 1u << 16, ROW_LOGITS = 1u << 17, ROW_VALID = 1u << 18 };
 // One tile = up to 128 consecutive rows of one level.  prev_first / prev_count: the tiles of the previous level;
 // wait_start: progress the previous level must have published before this tile does anything (0, all 33 cache
 // tensors, or PROG_DONE = its tokens as well).
+// kind_g: tile kind | first GEMM << 8 | end GEMM << 16 (halo tiles).  FULL: the whole column of its rows (known prefix,
+// teacher-forced logits).  Sampled levels are split: a HALO tile multiplies the gathered neighbour taps of a group of
+// GEMMs for up to 128 rows and stores per-row fp32 partial sums (no dependence on the rows' own chain, so it runs ahead,
+// a step behind the previous level); a CHAIN tile runs the dependent part of up to 32 rows -- nin_skip, centre tap,
+// epilogue, token -- and adds the partial sums.  part_row0: the tile's first row in the partial-sum buffer; h_first: a
+// chain tile's halo tiles (one per GEMM group, consecutive).
+enum { TILE_FULL = 0, TILE_CHAIN = 1, TILE_HALO = 2 };
 struct Tile {
-  int row_begin, nrows, prev_first, prev_count, wait_start, pad0, pad1, pad2;
+  int row_begin, nrows, prev_first, prev_count, wait_start, kind_g, part_row0, h_first;
 };
 
 struct TcParams {
@@ -116,6 +128,11 @@ struct TcParams {
   const float* bias;
   int b_uinit, b_nin;
   ps_lmconv_op ops[TC_NOPS];
+  const ps_lmconv_chunk* chunks_chain;
+  int n_chain_body, n_chain_total;
+  const ps_lmconv_chunk* chunks_halo;
+  short halo_first[33], part_col[33];
+  float* part;  // [2 x part_cap rows][LMT_PART_COLS] fp32 partial sums of the halo tiles
   unsigned long long raw_mask;  // bit t: cached tensor t is read through its raw third (by a dilated convolution)
   __half* act;
   const ps_lmconv_row* rows;
@@ -138,6 +155,8 @@ struct TcParams {
 
 struct TcSmem {
   uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[3], cfull;
+  uint64_t acc_empty[2];        // halo tiles: the epilogue has drained the accumulator (no centre-operand hand-off there)
+  uint64_t pfull[2], pempty[2];  // chain tiles: the partial sums of a GEMM have landed in / been read from their buffer
   uint32_t tmem_slot, pad_steps;
   uint32_t warp_steps[4];  // finished cache tensors per epilogue warp (the tile's progress is their minimum)
   Tile tile;
@@ -229,7 +248,25 @@ __device__ __forceinline__ void red_release_cta_shared_inc(uint32_t* p) {
 
 // Whole warp: returns once every tile of the previous level has published progress >= need; returns the smallest
 // progress seen (so the caller can skip later polls).  A wait of ~1 s trips the same watchdog as the mbarriers.
-__device__ __noinline__ unsigned int wait_progress(const unsigned int* prog, int first, int count, unsigned int need) {
+// developer aid: when the watchdog trips, every warp still inside wait_progress logs what it waits for (pinned host words)
+static __device__ __noinline__ void wedge_snapshot(int first, int count, unsigned int need, unsigned int seen, int tag) {
+  volatile unsigned int* h = g_wedge_host;
+  if (!h) return;
+  const unsigned int slot = atomicAdd(&g_wedge[7], 1u);
+  if (slot >= 256u) return;
+  volatile unsigned int* e = h + 8 + slot * 8;
+  e[0] = blockIdx.x;
+  e[1] = threadIdx.x;
+  e[2] = (unsigned int)first;
+  e[3] = (unsigned int)count;
+  e[4] = need;
+  e[5] = seen;
+  e[6] = (unsigned int)tag;
+  e[7] = 0xabcd0000u | slot;
+  __threadfence_system();
+}
+
+__device__ __noinline__ unsigned int wait_progress(const unsigned int* prog, int first, int count, unsigned int need, int tag = 0) {
   const int lane = threadIdx.x & 31;
   const long long t0 = clock64();
   for (unsigned int spins = 0;; ++spins) {
@@ -239,9 +276,15 @@ __device__ __noinline__ unsigned int wait_progress(const unsigned int* prog, int
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (v >= need) return v;
     if ((spins & 63u) == 63u) {
-      if (*(volatile unsigned int*)&g_wedge[0]) return 0xffffffffu;
+      if (*(volatile unsigned int*)&g_wedge[0]) {
+        if (lane == 0) wedge_snapshot(first, count, need, v, tag);
+        return 0xffffffffu;
+      }
       if (clock64() - t0 > 2000000000ll) {
-        if (lane == 0) wedge_report(0xffffffffu, need);
+        if (lane == 0) {
+          wedge_report(0xffffffffu, need);
+          wedge_snapshot(first, count, need, v, tag);
+        }
         return 0xffffffffu;
       }
     }
@@ -327,12 +370,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     const int t = (int)atomicAdd(p.sync, 1u);
     sm.tile_index = t;
     sm.tile = p.tiles[t];
+    g_blk_tag[blockIdx.x & 16383] = (unsigned int)t | ((unsigned int)(sm.tile.kind_g & 255) << 24);
     sm.warp_steps[0] = sm.warp_steps[1] = sm.warp_steps[2] = sm.warp_steps[3] = 0;
   }
-  for (int i = tid; i < p.n_total; i += TC_THREADS) sm.sched[i] = pack_chunk(p.chunks[i]);
   __syncthreads();
   const Tile tile = sm.tile;
   const int tile_index = sm.tile_index;
+  const int tkind = tile.kind_g & 255, hg0 = (tile.kind_g >> 8) & 255, hg1 = (tile.kind_g >> 16) & 255;
+  const bool is_chain = tkind == TILE_CHAIN, is_halo = tkind == TILE_HALO;
+  // the tile's chunk schedule: the whole column, its chain part, or the gathered taps of GEMMs [hg0, hg1)
+  const ps_lmconv_chunk* sched_src = is_halo ? p.chunks_halo + p.halo_first[hg0] : (is_chain ? p.chunks_chain : p.chunks);
+  const int n_sched_total = is_halo ? p.halo_first[hg1] - p.halo_first[hg0] : (is_chain ? p.n_chain_total : p.n_total);
+  const int n_sched_body = is_halo ? n_sched_total : (is_chain ? p.n_chain_body : p.n_body);
+  const int logit_first = is_chain ? p.n_chain_body : p.logit_first;
+  for (int i = tid; i < n_sched_total; i += TC_THREADS) sm.sched[i] = pack_chunk(sched_src[i]);
   const bool traced = tile_index == p.n_tiles - 1;
   const unsigned int* prog = p.sync + 16;
   // Ring geometry: the A tile of a stage holds only the tile's rows (rounded up to 8); the MMA still reads 128 rows
@@ -343,7 +394,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   const int a_bytes = a_rows * 128;
   const int slot_bytes = a_bytes + TC_W_BYTES;
   const int stage_bytes = 2 * slot_bytes;
-  const int nst = min(TC_MAX_STAGES, (TC_STAGES * TC_STAGE_BYTES) / stage_bytes);
+  // a chain tile keeps two partial-sum buffers behind its (short) ring
+  const int ring_cap = TC_STAGES * TC_STAGE_BYTES - (is_chain ? 2 * PART_BUF_BYTES : 0);
+  const int nst = min(TC_MAX_STAGES, ring_cap / stage_bytes);
+  unsigned char* pbuf = tiles + ring_cap;
   // byte offset of chunk i's slot in the ring
   auto slot_off = [&](int i) { return ((i >> 1) % nst) * stage_bytes + (i & 1) * slot_bytes; };
 
@@ -359,11 +413,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < nst; ++s) {
-        mbar_init(&sm.full[s], 66);  // per chunk: 32 arrivals of the row writers (a gather warp, or the weight producer's lanes for an operand that is not in the ring) + the weight copy
+        // per chunk: 32 arrivals of the row writers (a gather warp, or the weight producer's lanes for an operand that
+        // is not in the ring) + the weight copy; per stage use: one arrival of each of the four gather warps
+        mbar_init(&sm.full[s], 70);
         mbar_init(&sm.empty[s], 1);
       }
       for (int i = 0; i < 3; ++i) mbar_init(&sm.acc_full[i], 1);
       mbar_init(&sm.cfull, 4);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sm.acc_empty[i], 4);
+        mbar_init(&sm.pfull[i], 128);
+        mbar_init(&sm.pempty[i], 4);
+      }
       mbar_fence_init();
     }
     __syncwarp();
@@ -371,11 +432,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   }
   tc_fence_before();
   const int need_logits =
-      __syncthreads_or(tid < tile.nrows && (p.rows[tile.row_begin + tid].w2_flags & (ROW_SAMPLED | ROW_LOGITS)));
+      __syncthreads_or(!is_halo && tid < tile.nrows && (p.rows[tile.row_begin + tid].w2_flags & (ROW_SAMPLED | ROW_LOGITS)));
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, sm.tmem_slot, 0);
   if (tid == 0) TC_TRACE(7, 0);
-  const int nchunks = need_logits ? p.n_total : p.n_body;
+  const int nchunks = need_logits ? n_sched_total : n_sched_body;
 
   if (warp == 0) {
     // ===== weight producer: whole warp, warp-uniform values, one elected lane issues (see umma_f16_kblock) =====
@@ -406,8 +467,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     // ===== MMA issuer: the whole warp runs the loop with warp-uniform values; one elected lane issues =====
     const uint32_t ring_lo = umma_desc_lo(smem_u32(tiles));
     const uint32_t idesc0 = umma_idesc_f16(0);
-    const uint32_t reuse_lo0 = ring_lo + (uint32_t)(slot_off(p.logit_first) >> 4);
-    const uint32_t reuse_lo1 = ring_lo + (uint32_t)(slot_off(p.logit_first + 1) >> 4);
+    const uint32_t reuse_lo0 = ring_lo + (uint32_t)(slot_off(logit_first) >> 4);
+    const uint32_t reuse_lo1 = ring_lo + (uint32_t)(slot_off(logit_first + 1) >> 4);
     int st = 0;
     uint32_t ph = 0, cph = 0;
     uint2 nxt = sm.sched[0];
@@ -427,6 +488,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
           mbar_wait(&sm.cfull, cph);
           cph ^= 1u;
           tc_fence_after();
+        }
+        if (is_halo && !(flags & 1u)) {  // halo tile, first chunk of a GEMM: its accumulator has been drained
+          const int n = (int)((raw.y >> 26) & 63u) - hg0;
+          if (n >= 2) {
+            mbar_wait(&sm.acc_empty[n & 1], (uint32_t)((n >> 1) - 1) & 1u);
+            tc_fence_after();
+          }
         }
         if (lane == 0) TC_TRACE(0, i + h);
         const uint32_t idesc = idesc0 | (((p.debug & 16) ? 2u : ((raw.x >> 24) & 31u)) << 17);  // N >> 3 = w_rows / 8
@@ -457,7 +525,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     if (lane == 0) {
       unsigned int* mine = p.sync + 16 + tile_index;
       unsigned int published = 0;
-      while (published < PROG_DONE) {
+      const unsigned int target = is_halo ? (unsigned int)(hg1 - hg0) : (unsigned int)PROG_DONE;
+      while (published < target) {
         // the slowest epilogue warp's count (a sum over the warps would overstate it when one warp lags)
         const unsigned int done =
             min(min(ld_acquire_cta_shared(&sm.warp_steps[0]), ld_acquire_cta_shared(&sm.warp_steps[1])),
@@ -496,9 +565,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     const uint32_t dst_odd = smem_u32(tiles) + (rs + 4) * 128 + ((g ^ (rs + 4)) << 4);  // rows rs + 4 + 8m
     const int npair = (tile.nrows + 7) >> 3;  // row pairs (rs + 8m, rs + 4 + 8m) of this lane
     int seen = 0;                              // gathered chunks so far: this warp takes those with seen % 4 == gw
+    int cur_gemm = -1;                         // chain tiles: GEMM whose partial sums were requested last
     unsigned int verified = tile.prev_count ? 0u : 0xffffffffu;  // progress every earlier level is known to have reached
     if (verified < (unsigned int)tile.wait_start)
-      verified = wait_progress(prog, tile.prev_first, tile.prev_count, (unsigned int)tile.wait_start);
+      verified = wait_progress(prog, tile.prev_first, tile.prev_count, (unsigned int)tile.wait_start, tile_index | tkind << 24 | 1 << 28);
     for (int i = 0; i < nchunks; ++i) {
       const int st = (i >> 1) % nst;
       // EVERY gather warp waits for EVERY use of every ring stage, in ring order, whether or not it fills a chunk there.
@@ -509,8 +579,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       // overwrote a stage that had not been multiplied yet and its 32 arrivals landed in the wrong phase of `full`
       // -- wrong activations, and sooner or later an mbarrier arrival overflow = "unspecified launch failure"
       // (round 1's intermittent fault at batch 128; profiles/r02_launch_failure_rootcause.txt).
-      if (!(i & 1)) mbar_wait(&sm.empty[st], ((uint32_t)((i >> 1) / nst) & 1u) ^ 1u);
+      // ... and every gather warp ARRIVES on every use as well: the MMA warp cannot finish a stage use without it, so a
+      // gather warp that is held up elsewhere (a chain tile's wait for its halo tile, a progress wait) can never fall a
+      // phase BEHIND the ring either -- stage uses whose chunks nobody gathers (centre taps) would otherwise run past it.
+      if (!(i & 1)) {
+        mbar_wait(&sm.empty[st], ((uint32_t)((i >> 1) / nst) & 1u) ^ 1u);
+        if (lane == 0) mbar_arrive(&sm.full[st]);
+      }
       const Chunk ch = unpack_chunk(sm.sched[i]);
+      if (is_chain && ch.gemm != cur_gemm && ch.gemm < 32 && !(p.debug & 1024)) {
+        // Chain tile, first chunk of GEMM gg: bring the rows' partial sums of its gathered taps (written by the halo
+        // tile of the GEMM's group) into buffer gg & 1.  All four gather warps: thread t -> row t / 4, every 4th
+        // 16-byte group; group k of row r sits at group k ^ (r & 7) so the epilogue's 16-byte row reads spread over
+        // the banks.  Every gather thread passes every use of the two buffers in order (parity waits stay unambiguous).
+        const int gg = cur_gemm = ch.gemm;
+        if (!(p.debug & 2048)) wait_progress(prog, tile.h_first + gg / HALO_GROUP, 1, (unsigned int)(gg % HALO_GROUP + 1), tile_index | tkind << 24 | 2 << 28);
+        if (!(p.debug & 4096)) mbar_wait(&sm.pempty[gg & 1], ((uint32_t)(gg >> 1) & 1u) ^ 1u);
+        const int c0 = p.part_col[gg], ngrp = (p.part_col[gg + 1] - c0) >> 2;
+        const int row = t >> 2;
+        const float* src = p.part + (size_t)(tile.part_row0 + row) * LMT_PART_COLS + c0;
+        const uint32_t dst = smem_u32(pbuf) + (uint32_t)((gg & 1) * PART_BUF_BYTES + row * PART_ROW_BYTES);
+        const uint32_t nb = row < tile.nrows ? 16u : 0u;
+        for (int k = t & 3; k < ngrp; k += 4)
+          cp_async16_zfill(dst + (uint32_t)((k ^ (row & 7)) << 4), nb ? (const void*)(src + 4 * k) : (const void*)p.part, nb);
+        if (p.debug & 16384) {
+          cp_async_commit();
+          cp_async_wait<0>();
+          mbar_arrive(&sm.pfull[gg & 1]);
+        } else {
+          cp_async_arrive_noinc(&sm.pfull[gg & 1]);
+        }
+      }
       if (ch.a_kind != A_GATHER && ch.a_kind != A_CENTRE) continue;
       if ((seen++ & 3) != gw) continue;
       const int kg = ch.kc * 8 + g;
@@ -525,8 +624,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         off = (((tr - 1) * 32 + (tap - 3 * tr - 1)) * dil + ch.a_tensor * LMT_CELLS) * (LMT_ACT * 2) + (ch.ch_off8 + c8) * 16;
         // GEMM j reads tensors the neighbours wrote at step <= j.  Waiting until the previous level is a step further
         // (progress >= j + 2) also proves, by induction over the levels, that every earlier level has reached j + 1.
-        const unsigned int need = (unsigned int)min(ch.gemm + 2, LMT_TENSORS);
-        if (verified < need) verified = wait_progress(prog, tile.prev_first, tile.prev_count, need);
+        // (A halo tile's previous level is the chain of the level before, which started only when everything older was
+        // complete: progress >= j + 1 is enough there.)
+        const unsigned int need = (unsigned int)min(ch.gemm + (is_halo ? 1 : 2), LMT_TENSORS);
+        if (verified < need) verified = wait_progress(prog, tile.prev_first, tile.prev_count, need, tile_index | tkind << 24 | 3 << 28);
       } else {
         bitpos = kg < ch.cin8 ? 27 : 31;
         off = ch.a_tensor * LMT_CELLS * (LMT_ACT * 2) + (ch.ch_off8 + kg) * 16;
@@ -564,10 +665,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     e.actrow = p.act + ((size_t)b * LMT_TENSORS * LMT_CELLS + cell) * LMT_ACT;
     const float* bias = p.bias;
     int g = 0;  // GEMM counter
+    // chain tiles: the partial sums of GEMM gi's gathered taps wait in shared-memory buffer gi & 1 (rows 0..31 only)
+    const bool prow_ok = is_chain && r < CHAIN_ROWS && !(p.debug & 1024);  // warp-uniform
+    const unsigned char* prow = pbuf + r * PART_ROW_BYTES;
+    auto part_wait = [&](int gi) {
+      if (is_chain && !(p.debug & (1024 | 8192))) mbar_wait(&sm.pfull[gi & 1], (uint32_t)(gi >> 1) & 1u);
+    };
+    auto part_add16 = [&](float* v, int gi, int c16) {  // v[0..16) += columns [16 c16, 16 c16 + 16) of GEMM gi's partial sums
+      if (prow_ok) {
+        const unsigned char* b = prow + (gi & 1) * PART_BUF_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 f = *reinterpret_cast<const float4*>(b + (((4 * c16 + q) ^ (r & 7)) << 4));
+          v[4 * q] += f.x;
+          v[4 * q + 1] += f.y;
+          v[4 * q + 2] += f.z;
+          v[4 * q + 3] += f.w;
+        }
+      }
+    };
+    auto part_release = [&](int gi) {
+      if (is_chain && !(p.debug & 1024)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.pempty[gi & 1]);
+      }
+    };
+
+    if (is_halo) {
+      // ---- halo tile: each GEMM's accumulator (the gathered taps only) goes to the partial-sum buffer as it is ----
+      float* out_row = p.part + (size_t)(tile.part_row0 + r) * LMT_PART_COLS;
+      for (int gi = hg0; gi < hg1; ++gi) {
+        const int n = gi - hg0;
+        const uint32_t col0 = (uint32_t)(gi & 1) * 160u;
+        mbar_wait(&sm.acc_full[gi & 1], (uint32_t)(n >> 1) & 1u);
+        tc_fence_after();
+        const int c0 = p.part_col[gi], ncol = p.part_col[gi + 1] - c0;
+        for (int c = 0; c < ncol; c += 16) {
+          float v[16];
+          tmem_ld16_nowait(e.tlane + col0 + c, v);
+          tmem_ld_wait();
+          if (e.valid) {
+            float4* d = reinterpret_cast<float4*>(out_row + c0 + c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) __stcg(d + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.acc_empty[gi & 1]);
+        e.step_done();
+      }
+    } else {
 
     // the first layer reads the neighbours' tokens: a level with sampled cells starts when the previous one has drawn
     if (tile.wait_start && tile.prev_count)
-      wait_progress(prog, tile.prev_first, tile.prev_count, (unsigned int)tile.wait_start);
+      wait_progress(prog, tile.prev_first, tile.prev_count, (unsigned int)tile.wait_start, tile_index | tkind << 24 | 4 << 28);
 
     // ---- u_init over [one-hot(code) | ones]: a gather of weight rows (mask A), then PONO ----
     {
@@ -627,6 +779,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
           for (int j = 0; j < 5; ++j) tmem_ld16_nowait(e.tlane + col0 + 16 * j, x + 16 * j);
           tmem_ld_wait();
           add_bias80(x, bias + op.b_in);
+          part_wait(g);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) part_add16(x + 16 * j, g, j);
+          part_release(g);
           pono80(x);
           if (op.a >= 0) {
 #pragma unroll
@@ -657,6 +813,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
           for (int j = 0; j < 5; ++j) tmem_ld16_nowait(e.tlane + col0 + 16 * j, a + 16 * j);
           tmem_ld_wait();
           add_bias80(a, bias + op.b_out);
+          part_wait(g);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) part_add16(a + 16 * j, g, j);
           pono80(a);
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
@@ -665,6 +824,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
             tmem_ld16_nowait(e.tlane + COL_OG + 16 * j, o);
             tmem_ld_wait();
             add_bias16(gt, bias + op.b_out + 80 + 16 * j);
+            part_add16(gt, g, 5 + j);
+            if (j == 4) part_release(g);
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = fmaf(a[16 * j + i], __fdividef(1.0f, 1.0f + __expf(-gt[i])), o[i]);
             tmem_st16_nowait(e.tlane + COL_OG + 16 * j, o);
@@ -685,6 +846,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         for (int j = 0; j < 5; ++j) tmem_ld16_nowait(e.tlane + col0 + 16 * j, x + 16 * j);
         tmem_ld_wait();
         add_bias80(x, bias + op.b_in);
+        part_wait(g);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) part_add16(x + 16 * j, g, j);
+        part_release(g);
         pono80(x);
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
@@ -703,7 +868,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       // the ring stages of quarter 0's two chunks.  Their last users (body chunks) completed before the last
       // accumulator barrier fired, and no later chunk writes rows into them. ----
       {
-        const int first = p.logit_first;
+        const int first = logit_first;
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
           float o[16], pp[16], nn;
@@ -780,6 +945,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       tc_fence_before();
     }
     e.step_done();  // progress PROG_DONE: the tile's tokens (if any) are in `codes`
+    }  // !is_halo
   }
   __syncthreads();
   if (tid == 0) TC_TRACE(7, 1);
@@ -799,9 +965,14 @@ void ps_lmconv_tc_set_trace(void* dev_buffer) { g_tc_trace = (long long*)dev_buf
 
 // activation cache + the launch's tile table and progress words
 static size_t tc_act_bytes(int B) { return (size_t)(B > 0 ? B : 0) * LMT_TENSORS * LMT_CELLS * LMT_ACT * sizeof(__half); }
-static size_t tc_max_tiles(int B) { return (size_t)(B > 0 ? B : 0) * LMT_CELLS + 1; }
+// every row has at most one chain tile and 8 halo tiles of its own, usually far fewer
+static size_t tc_max_tiles(int B) { return (size_t)(B > 0 ? B : 0) * LMT_CELLS * 2 + 64; }
+// rows of one sampled level whose partial sums the buffer holds (two levels in flight); a wider level runs unsplit
+static size_t tc_part_rows(int B) { return align_up((size_t)std::max(256, (B > 0 ? B : 0) * 64), 128); }
+static size_t tc_part_bytes(int B) { return 2 * tc_part_rows(B) * LMT_PART_COLS * sizeof(float); }
 size_t ps_lmconv_tc_cache_bytes(int B) {
-  return align_up(tc_act_bytes(B), 256) + align_up(tc_max_tiles(B) * sizeof(Tile), 256) + (tc_max_tiles(B) + 16) * sizeof(unsigned int);
+  return align_up(tc_act_bytes(B), 256) + align_up(tc_max_tiles(B) * sizeof(Tile), 256) +
+         align_up((tc_max_tiles(B) + 16) * sizeof(unsigned int), 256) + tc_part_bytes(B);
 }
 
 // Dependency levels (host).  A cell reads, through its three masks, cells generated earlier; it sits one level above
@@ -987,6 +1158,16 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   p.chunks = plan->chunks;
   p.n_body = plan->n_chunks_body;
   p.n_total = plan->n_chunks_total;
+  const bool can_split = plan->chunks_chain && plan->chunks_halo && plan->part_col[32] == LMT_PART_COLS &&
+                         plan->n_chain_total <= TC_MAX_CHUNKS && plan->n_chain_body % 2 == 0 && plan->n_chain_total % 2 == 0;
+  p.chunks_chain = plan->chunks_chain;
+  p.n_chain_body = plan->n_chain_body;
+  p.n_chain_total = plan->n_chain_total;
+  p.chunks_halo = plan->chunks_halo;
+  for (int i = 0; i < 33; ++i) {
+    p.halo_first[i] = (short)plan->halo_first[i];
+    p.part_col[i] = (short)plan->part_col[i];
+  }
   p.logit_first = plan->epi_first[32];
   p.w_uinit = (const __half*)plan->w_uinit;
   p.bias = plan->bias;
@@ -1013,10 +1194,58 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   std::vector<Tile> tiles;
   const int exp_bits = getenv("PS_TC_EXP") ? atoi(getenv("PS_TC_EXP")) : 0;  // developer aid: scheduling experiments
   int prev_first = 0, prev_count = 0;
+  if (exp_bits & 8) n_levels = first_b_level;  // timing aid: the known prefix alone
   for (int l = 0; l < n_levels; ++l) {
     const int r0 = level_offsets_host[l], r1 = level_offsets_host[l + 1];
     PS_CHECK_ARG(r1 >= r0);
     if (r1 == r0) continue;
+    // A sampled level (sampling mode) is split: halo tiles (<= 128 rows x a group of GEMMs: the gathered neighbour
+    // taps, as per-row partial sums) first, then chain tiles (<= 32 rows: what depends on the rows' own column).  Chain
+    // tiles wait for the previous level's CHAIN tiles (its tokens) and for their own halo tiles; halo tiles follow the
+    // previous level's chain one step behind.  The partial sums of two consecutive levels alternate between the two
+    // halves of the buffer: level l + 1's halo tiles start when level l's chain runs, which is after level l - 1's.
+    const int rows_l = r1 - r0;
+    const bool split = l >= first_b_level && can_split && !(exp_bits & 16) && uniforms && !logits_out &&
+                       (size_t)rows_l <= tc_part_rows(B);
+    if (split) {
+      const int part_base = (int)(((l - first_b_level) & 1) * tc_part_rows(B));
+      const int wait = l == first_b_level ? LMT_TENSORS : ((exp_bits & 32) ? PROG_DONE : 0);  // 32: halo tiles do not run ahead
+      const int n_hrow = (rows_l + 127) / 128, n_grp = (32 + HALO_GROUP - 1) / HALO_GROUP;
+      const int h_first = (int)tiles.size();
+      for (int hr = 0; hr < n_hrow; ++hr)
+        for (int gr = 0; gr < n_grp; ++gr) {
+          Tile tl;
+          memset(&tl, 0, sizeof(tl));
+          tl.row_begin = r0 + hr * 128;
+          tl.nrows = std::min(128, r1 - tl.row_begin);
+          tl.prev_first = prev_first;
+          tl.prev_count = prev_count;
+          tl.wait_start = wait;
+          tl.kind_g = TILE_HALO | (gr * HALO_GROUP) << 8 | std::min(32, (gr + 1) * HALO_GROUP) << 16;
+          tl.part_row0 = part_base + hr * 128;
+          tiles.push_back(tl);
+        }
+      const int c_first = (int)tiles.size();
+      for (int hr = 0; hr < n_hrow; ++hr) {
+        const int hb = r0 + hr * 128, he = std::min(r1, hb + 128);
+        for (int cb = hb; cb < he; cb += CHAIN_ROWS) {
+          Tile tl;
+          memset(&tl, 0, sizeof(tl));
+          tl.row_begin = cb;
+          tl.nrows = std::min(CHAIN_ROWS, he - cb);
+          tl.prev_first = prev_first;
+          tl.prev_count = prev_count;
+          tl.wait_start = l == first_b_level ? LMT_TENSORS : PROG_DONE;
+          tl.kind_g = TILE_CHAIN;
+          tl.part_row0 = part_base + (cb - r0);
+          tl.h_first = h_first + hr * n_grp;
+          tiles.push_back(tl);
+        }
+      }
+      prev_first = c_first;
+      prev_count = (int)tiles.size() - c_first;
+      continue;
+    }
     // The prefix levels overlap each other, so their tiles are full (fewest SMs per level).  A sampled level runs
     // alone and its time is one tile's latency: small tiles get a deeper operand ring and there are SMs to spare.
     int rpt = 128;
@@ -1050,6 +1279,7 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   char* tail = (char*)cache + align_up(tc_act_bytes(B), 256);
   Tile* tiles_dev = (Tile*)tail;
   unsigned int* sync_dev = (unsigned int*)(tail + align_up(tc_max_tiles(B) * sizeof(Tile), 256));
+  p.part = (float*)((char*)sync_dev + align_up((tc_max_tiles(B) + 16) * sizeof(unsigned int), 256));
   // The tile table is staged in a pinned buffer that outlives the call (one per host thread, grown on demand): the
   // copy is asynchronous and nothing here waits for the stream.  A second call from the same thread reuses the buffer
   // only after the previous call's copy has left it (event).

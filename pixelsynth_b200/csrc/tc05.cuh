@@ -62,12 +62,32 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return done;
 }
 
+// developer aid: blockIdx -> what the block works on (lmconv: its tile ticket), for the waiter snapshot
+static __device__ unsigned int g_blk_tag[16384];
+
+static __device__ __noinline__ void mbar_snapshot(uint32_t bar, uint32_t parity) {
+  volatile unsigned int* h = g_wedge_host;
+  if (!h) return;
+  if ((g_blk_tag[blockIdx.x & 16383] >> 24) != 1u) return;  // chain tiles only
+  const unsigned int slot = atomicAdd(&g_wedge[6], 1u);
+  if (slot >= 64u) return;
+  volatile unsigned int* e = h + 8 + 256 * 8 + slot * 4;
+  e[0] = blockIdx.x;
+  e[1] = threadIdx.x;
+  e[2] = bar;
+  e[3] = parity | ((g_blk_tag[blockIdx.x & 16383] & 0xffffffu) << 4) | 0x80000000u;
+  __threadfence_system();
+}
+
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   for (int spins = 0;; ++spins) {
     if (mbar_try_wait(bar, parity)) return;
     if ((spins & 63) == 63) {
-      if (*(volatile unsigned int*)&g_wedge[0]) return;
+      if (*(volatile unsigned int*)&g_wedge[0]) {
+        if ((threadIdx.x & 31) == 0) mbar_snapshot(smem_u32(bar), parity);
+        return;
+      }
       if (clock64() - t0 > 2000000000ll) {
         wedge_report(smem_u32(bar), parity);
         return;

@@ -40,7 +40,11 @@ class _Plan(ctypes.Structure):
     _fields_ = [("wblob", ctypes.c_void_p), ("chunks", ctypes.c_void_p), ("n_chunks_body", ctypes.c_int),
                 ("n_chunks_total", ctypes.c_int), ("epi_first", ctypes.c_int * MAX_GEMMS), ("w_uinit", ctypes.c_void_p),
                 ("bias", ctypes.c_void_p), ("b_uinit", ctypes.c_int), ("b_nin", ctypes.c_int), ("ops", _Op * 18),
-                ("raw_mask", ctypes.c_uint64)]
+                ("raw_mask", ctypes.c_uint64),
+                # the same schedule split for the sampled levels: `chain` = what depends on the row's own column (nin_skip,
+                # centre tap, nin_out), `halo` = the gathered neighbour taps, whose per-row partial sums other CTAs compute
+                ("chunks_chain", ctypes.c_void_p), ("n_chain_body", ctypes.c_int), ("n_chain_total", ctypes.c_int),
+                ("chunks_halo", ctypes.c_void_p), ("halo_first", ctypes.c_int * 33), ("part_col", ctypes.c_int * 33)]
 
 
 assert ctypes.sizeof(_Chunk) == 16 and ctypes.sizeof(_Row) == 16
@@ -197,6 +201,41 @@ class LmconvB200:
         self.wblob = torch.from_numpy(np.concatenate(blobs)).to(device)
         self.chunks = torch.from_numpy(np.frombuffer(b"".join(bytes(c) for c in chunks), dtype=np.uint8).copy()).to(device)
         self.bias = torch.cat(bs).to(device).contiguous()
+        # ---- chain / halo split of the same chunk list (csrc/lmconv_tc.cu, sampled levels) ----
+        def clone(c):
+            d = _Chunk()
+            ctypes.memmove(ctypes.byref(d), ctypes.byref(c), ctypes.sizeof(_Chunk))
+            return d
+
+        chain, halo, halo_first, part_col = [], [], [], []
+        col = 0
+        for g in range(32):
+            mine = [c for c in chunks[:self.plan.n_chunks_body] if c.gemm == g]
+            gath = [clone(c) for c in mine if c.a_kind == A_GATHER]
+            halo_first.append(len(halo))
+            gath[-1].flags |= 2 | ((g & 1) << 2)          # the last gathered chunk completes the halo accumulator
+            halo += gath
+            part_col.append(col)
+            col += mine[0].w_rows                          # 80 or 160 partial-sum columns per row
+            for c in mine:
+                if c.a_kind == A_GATHER:
+                    continue
+                d = clone(c)
+                if d.a_kind == A_TMEM and d.kc == 0:
+                    d.flags &= ~1                          # nothing was accumulated before the centre tap any more
+                chain.append(d)
+        halo_first.append(len(halo))
+        part_col.append(col)
+        self.part_cols = col
+        self.plan.n_chain_body = len(chain)
+        chain += [clone(c) for c in chunks[self.plan.n_chunks_body:]]
+        self.plan.n_chain_total = len(chain)
+        assert self.plan.n_chain_body % 2 == 0 and self.plan.n_chain_total % 2 == 0 and all(h % 2 == 0 for h in halo_first)
+        for i in range(33):
+            self.plan.halo_first[i], self.plan.part_col[i] = halo_first[i], part_col[i]
+        pack = lambda cs: torch.from_numpy(np.frombuffer(b"".join(bytes(c) for c in cs), dtype=np.uint8).copy()).to(device)
+        self.chunks_chain, self.chunks_halo = pack(chain), pack(halo)
+        self.plan.chunks_chain, self.plan.chunks_halo = self.chunks_chain.data_ptr(), self.chunks_halo.data_ptr()
         self.plan.wblob, self.plan.chunks = self.wblob.data_ptr(), self.chunks.data_ptr()
         self.plan.w_uinit, self.plan.bias = self.w_uinit.data_ptr(), self.bias.data_ptr()
         self._cache = None

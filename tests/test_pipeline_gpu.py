@@ -199,3 +199,30 @@ def test_gen_scene_sweep(model, oracle):
         assert np.array_equal(s["background_mask"].cpu().numpy(), oracle.bgmask(idx, 13))
     finally:
         model.opt.model_setting = "gen_paired_img"
+
+
+def test_soak_batch64_all_views():
+    """Round 1's intermittent launch failure (profiles/r02_launch_failure_rootcause.txt) showed up as a CUDA fault or as
+    silently different tokens at batch 64-128.  30 full steps at batch 64 with all eight circle views in the batch: no
+    fault, no wedged barrier, and bit-identical output every step."""
+    from bench import make_batch as bench_batch
+    from pixelsynth_b200 import _lib
+    from pixelsynth_b200.models.z_buffermodel import ZbufferModelPts
+
+    B = 64
+    m = ZbufferModelPts(make_opt())
+    hb = bench_batch(B, [i % 8 for i in range(B)])
+    db = {"images": [t.cuda() for t in hb["images"]], "cameras": [{k: v.cuda() for k, v in c.items()} for c in hb["cameras"]]}
+    g = torch.Generator().manual_seed(3)
+    noise = torch.randn(16, B, 20, generator=g).cuda()
+    uniforms = torch.rand(B, 1024, generator=g)
+    ref = None
+    for step in range(30):
+        out = m.forward(db, noise=noise, uniforms=uniforms)[1]["PredImg"]
+        if ref is None:
+            ref = out.clone()
+        else:
+            assert torch.equal(out, ref), "step %d differs from step 0" % step
+    torch.cuda.synchronize()
+    _lib.check_wedge("soak")
+    assert torch.isfinite(ref).all()

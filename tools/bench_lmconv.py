@@ -33,8 +33,32 @@ best = None
 for rep in range(args.reps + 1):
     _lib.kernel_time_ms(None)
     L.ps_timing_enable(1)
-    out = model.sample(codes, order, words, smask, uniforms, 0.7)
-    torch.cuda.synchronize()
+    try:
+        out = model.sample(codes, order, words, smask, uniforms, 0.7)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        import ctypes
+        info = (ctypes.c_uint * 8)()
+        print("FAULT rep %d: %s; wedge=%d info=%s" % (rep, str(e).splitlines()[0], L.ps_wedge_poll(info), [hex(x) for x in info]), flush=True)
+        NW = 8 + 256 * 8 + 64 * 4
+        log = (ctypes.c_uint * NW)()
+        L.ps_wedge_log(log, NW)
+        for k in range(256):
+            w = log[8 + 8 * k: 16 + 8 * k]
+            m = log[8 + 2048 + 4 * k: 12 + 2048 + 4 * k] if k < 64 else [0, 0, 0, 0]
+            if m[3] >> 31:
+                print("  mbar waiter: block %d thread %d (warp %d) barrier smem 0x%x (TcSmem+%d) parity %d; tile %d" %
+                      (m[0], m[1], m[1] // 32, m[2], m[2] - 0x36400, m[3] & 1, (m[3] >> 4) & 0x7ffffff), flush=True)
+            if w[7] >> 16 == 0xabcd:
+                print("  waiter: block %d thread %d waits tiles [%d,+%d) >= %d (saw %d); own tile %d kind %d site %d" %
+                      (w[0], w[1], w[2], w[3], w[4], w[5], w[6] & 0xffffff, (w[6] >> 24) & 15, w[6] >> 28), flush=True)
+        import os
+        os._exit(3)
+    if L.ps_wedge_poll(None):
+        import ctypes
+        info = (ctypes.c_uint * 8)()
+        L.ps_wedge_poll(info)
+        print("WEDGED rep %d: info=%s" % (rep, [hex(x) for x in info]), flush=True)
     L.ps_timing_enable(0)
     ms, n = _lib.kernel_time_ms("lmconv_tc_kernel")
     if rep > 0:

@@ -56,6 +56,12 @@ def parse():
     ap.add_argument("--view", type=int, default=-1,
                     help="-1 (default): image i of rank r renders circle view (i + r) mod 8, so every rank carries the same "
                          "mix of all 8 views; 0..7: every image renders that one view")
+    ap.add_argument("--workload", default="views", choices=["views", "scene"],
+                    help="views (default, the headline): one novel view per image, BASELINE configs[1]/[3]; scene: BASELINE "
+                         "configs[4], every image sweeps a scene (gen_scene, refinement decoder included) -- a step is the whole "
+                         "sweep of --batch images per GPU (default 32 = 256 images over 8 GPUs)")
+    ap.add_argument("--directions", nargs="+", default=["R", "L"], help="scene sweep directions (scripts/demo_scene.sh uses 10)")
+    ap.add_argument("--num_split", type=int, default=2, help="scene sweep splits per direction (scripts/demo_scene.sh: 32)")
     ap.add_argument("--cpu-tokens", type=int, default=16, help="sampler tokens timed per step for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -259,10 +265,103 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_scene(args):
+    """BASELINE configs[4]: batched scene sweeps sharded by image over the GPUs (no data-path collective).  One step =
+    every image of the rank's batch rendered along all `--directions` x `--num_split` poses over its growing point
+    cloud; value = rendered views/s of the whole job (inputs resident in HBM), e2e adds the H2D of the images / cameras
+    and the D2H of every rendered view."""
+    import torch
+    import torch.distributed as dist
+    from pixelsynth_b200 import _lib
+    from pixelsynth_b200.models.z_buffermodel import ZbufferModelPts
+
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=3))
+        os.environ.setdefault("PS_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+    B = args.batch if any(a.startswith("--batch") for a in sys.argv[1:]) else 32
+    opt = make_opt(model_setting="gen_scene", directions=list(args.directions), num_split=args.num_split,
+                   sequential_outpainting=False)
+    model = ZbufferModelPts(opt, device=dev)
+    from pixelsynth_b200 import synthetic
+    from util import demo_cameras
+    K, Kinv, RT1, RT1inv, _, _ = [torch.from_numpy(m) for m in demo_cameras(B, "identity", 0)]
+    img = synthetic.synth_image(B, 100 + rank)                      # every rank owns different images
+    host = {"images": [img], "cameras": [{"K": K, "Kinv": Kinv, "P": RT1, "Pinv": RT1inv}]}
+    resident = {"images": [img.to(dev)], "cameras": [{k: v.to(dev) for k, v in host["cameras"][0].items()}]}
+    pinned = {"images": [img.pin_memory()], "cameras": [{k: v.pin_memory() for k, v in host["cameras"][0].items()}]}
+    g = torch.Generator().manual_seed(1 + rank)
+    noise, uniforms = torch.randn(16, B, 20, generator=g).to(dev), torch.rand(B, 1024, generator=g)
+    views = sum(model._splits(d) + 1 for d in args.directions)
+    h_out = torch.empty((views, B, 3, W, W)).pin_memory()
+
+    def step(batch, fetch):
+        _, out = model.forward(batch, noise=noise, uniforms=uniforms)
+        if fetch:
+            for i, k in enumerate(k for k in out if k.startswith("PredImg_")):
+                h_out[i].copy_(out[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.lib().ps_launch_count_reset()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        _lib.check_wedge("bench.py")
+        ms, launches = e0.elapsed_time(e1), _lib.lib().ps_launch_count()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches = timed(lambda: step(resident, False))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(lambda: step(pinned, True))
+    cloud = int(model.last_scene[-1]["cloud"].shape[2])
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    total = views * B * world * args.steps
+    print(json.dumps({
+        "metric": METRIC, "value": total / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4]: scene sweep (gen_scene, z_buffermodel.py:421-592) with the refinement decoder, "
+                               "%d images per GPU in lock step, directions %s, num_split %d = %d dependent views per image; "
+                               "sharded by image, no collective" % (B, " ".join(args.directions), args.num_split, views),
+                   "views_per_image": views, "images_per_gpu": B, "final_cloud_points": cloud,
+                   "weights": "seeded random init of the reference architecture"},
+        "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(img.numel() * 4 + 4 * 64 * B),
+                "d2h_bytes_per_step": int(h_out.numel() * 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "scene":
+        return run_scene(args)
 
     import torch
     import torch.distributed as dist

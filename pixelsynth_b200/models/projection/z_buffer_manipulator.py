@@ -55,6 +55,22 @@ class PtsManipulator(nn.Module):
         return out, bg
 
     # -- z_buffer_manipulator.py:221-266 ------------------------------------------------------
+    @staticmethod
+    def _compact(sel, x):
+        """Per-image stream compaction for a batch whose images keep DIFFERENT numbers of points: x (B,C,P), sel (B,P)
+        bool -> (B,C,n_max) with image b's selected columns first, in order, and ZERO columns behind them.  A zero
+        homogeneous point stays zero under every camera matrix, so |z| < EPS parks it at (-10, 10, 10) by the
+        reference's own rule (z_buffer_manipulator.py:250-261): padding never reaches the rasteriser, and with equal
+        counts (batch 1 always) the result is exactly the reference's boolean-mask `.view(bs, c, -1)`."""
+        bs, c, _ = x.shape
+        n = sel.sum(1)
+        n_max = int(n.max())            # one small device->host read per view (the reference reads three)
+        rank = sel.cumsum(1) - 1
+        dst = torch.where(sel, rank, torch.full_like(rank, n_max))
+        out = x.new_zeros((bs, c, n_max + 1))
+        out.scatter_(2, dst.unsqueeze(1).expand(bs, c, -1), x)
+        return out[:, :, :n_max].contiguous()
+
     def project_pts_cumulative(self, pts3D, K, K_inv, RT_cam1, RTinv_cam1, RT_cam2, RTinv_cam2, prior_point_cloud=None,
                                last_background_mask=None, RTinv_cam3=None):
         """pts3D: full-grid depth (B,1,P); the reference passes the already-masked depth, here the mask is
@@ -64,8 +80,12 @@ class PtsManipulator(nn.Module):
         bs = pts.shape[0]
         if last_background_mask is not None:
             sel = last_background_mask.view(bs, -1)
-            pts = pts[sel].view(bs, -1, 3)
-            xyp = xyp.permute(0, 2, 1)[sel].view(bs, -1, 4).permute(0, 2, 1)
+            xyp = self._compact(sel, xyp)
+            # the padded tail must come out parked like any |z| < EPS point: (x, y, z) = (-10, 10, 10)
+            pts = self._compact(sel, pts.permute(0, 2, 1))
+            tail = torch.arange(pts.shape[2], device=pts.device)[None, :] >= sel.sum(1)[:, None]
+            park = pts.new_tensor([-10.0, 10.0, 10.0])[None, :, None]
+            pts = torch.where(tail[:, None, :], park, pts).permute(0, 2, 1).contiguous()
         if prior_point_cloud is not None:
             mats3 = torch.stack([K, RT_cam2, RTinv_cam3], 1).to(torch.float32).contiguous()
             pts2, xyp2 = torch.ops.pixelsynth_b200.project_cloud(prior_point_cloud, mats3, EPS)
@@ -76,13 +96,16 @@ class PtsManipulator(nn.Module):
     # -- z_buffer_manipulator.py:184-219 ------------------------------------------------------
     def forward_justpts_cumulative(self, src1, pred_pts, K, K_inv, RT_cam1, RTinv_cam1, RT_cam2, RTinv_cam2,
                                    prior_point_cloud, src2, last_background_mask, RTinv_cam3):
+        """Batches are allowed (BASELINE config 5): the images of a batch append different numbers of newly outpainted
+        pixels, so clouds and features are zero-padded per image (see _compact); the reference's boolean-mask views only
+        work when the counts agree, which is why it renders scenes one image at a time."""
         bs, c, w, h = src1.size()
         if last_background_mask is not None:
             last_background_mask = last_background_mask.view(bs, 1, -1)
         pred_pts = pred_pts.view(bs, 1, -1)
         src1 = src1.view(bs, c, -1)
         if src2 is not None:
-            src1 = src1[last_background_mask.repeat(1, c, 1)].view(bs, c, -1)
+            src1 = self._compact(last_background_mask.view(bs, -1), src1)
             src = torch.cat([src1, src2.view(bs, c, -1)], 2)
         else:
             src = src1

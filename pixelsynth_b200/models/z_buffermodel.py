@@ -239,10 +239,12 @@ class ZbufferModelPts(nn.Module):
     def forward_scene(self, batch, netD=None, noise=None, uniforms=None):
         """gen_scene: a sweep of views per direction over ONE growing point cloud.  Every rendered view is fed back as
         the next source image; only the pixels a view had to outpaint are appended to the cloud
-        (PtsManipulator.forward_justpts_cumulative).  Batch size 1, as in the reference."""
+        (PtsManipulator.forward_justpts_cumulative).  The reference renders one image at a time (its (1,4,4) pose
+        matrices are bmm'ed with the batch); here a batch of B images sweeps in lock step
+        (BASELINE config 5): every image gets the same relative camera motion applied to its OWN input pose, the clouds
+        are ragged per image (zero-padded, see PtsManipulator._compact), and image b of the batch equals what a batch-1
+        call on image b returns."""
         K, K_inv, input_RT, input_RTinv, input_img = self.process_batch(batch)
-        if input_img.shape[0] != 1:
-            raise ValueError("gen_scene renders one image at a time (the reference's cameras are built for batch 1)")
         if _get(self.opt, "no_outpainting", False):
             raise NotImplementedError("no_outpainting (3-channel decoder, SynSin baseline) is not the shipped configuration")
         min_z, max_z = float(_get(self.opt, "min_z")), float(_get(self.opt, "max_z"))
@@ -279,7 +281,9 @@ class ZbufferModelPts(nn.Module):
                 outputs["FeaturesImg_" + tag] = gen_fs
                 if kind == "far" or (sequential and num == num_split):
                     outputs["PredDepthImg_" + tag] = depth
-                    outputs["ForegroundImg_" + tag] = (~bg).repeat(input_img.shape[0], 1, 1, 1).float()
+                    nb = input_img.shape[0]   # the reference's `(~bg).repeat(B,1,1,1)` quirk, as a broadcast view for B > 1
+                    outputs["ForegroundImg_" + tag] = (~bg).repeat(nb, 1, 1, 1).float() if nb == 1 else \
+                        (~bg).float().unsqueeze(0).expand(nb, -1, -1, -1)
                     last_dir = direction
                 current_img, cloud, feats, last_bg, last_out_inv, last_num = gen_img, new_cloud, new_feats, bg, dst_inv, num
         return {}, outputs

@@ -192,3 +192,19 @@ def test_reference_import_paths_resolve_to_the_mirrors():
     assert importlib.import_module("models.layers.z_buffer_layers").RasterizePointsXYsBlending is not None
     top = importlib.import_module("demo")
     assert top.main is demo.main
+
+
+def test_ragged_cloud_compaction_pads_with_zero_points():
+    """PtsManipulator._compact (batched gen_scene): image b's selected columns first, in order, zero columns behind."""
+    from pixelsynth_b200.models.projection.z_buffer_manipulator import PtsManipulator
+
+    x = torch.arange(2 * 3 * 6, dtype=torch.float32).view(2, 3, 6) + 1
+    sel = torch.tensor([[1, 0, 1, 1, 0, 0], [0, 1, 0, 0, 0, 0]], dtype=torch.bool)
+    out = PtsManipulator._compact(sel, x)
+    assert out.shape == (2, 3, 3)
+    assert torch.equal(out[0], x[0][:, [0, 2, 3]])
+    assert torch.equal(out[1, :, 0], x[1][:, 1]) and (out[1, :, 1:] == 0).all()
+    # equal counts (the reference's only working case): exactly the boolean-mask view
+    sel2 = torch.tensor([[1, 0, 1, 0, 0, 0], [0, 1, 0, 0, 0, 1]], dtype=torch.bool)
+    ref = x[sel2.unsqueeze(1).repeat(1, 3, 1)].view(2, 3, -1)
+    assert torch.equal(PtsManipulator._compact(sel2, x), ref)

@@ -226,3 +226,42 @@ def test_soak_batch64_all_views():
     torch.cuda.synchronize()
     _lib.check_wedge("soak")
     assert torch.isfinite(ref).all()
+
+
+def test_gen_scene_batched_equals_single(model):
+    """BASELINE config 5: a BATCH of images sweeps a scene in lock step (the reference renders scenes at batch 1 only).
+    The clouds are ragged per image -- the two images outpaint different numbers of pixels -- and zero-padded; image b
+    of the batched sweep must equal the batch-1 sweep of image b: splat outputs bit-exact, refined images equal."""
+    from pixelsynth_b200 import synthetic
+
+    model.opt.model_setting = "gen_scene"
+    # 'S' = the translation circle: what a view uncovers depends on the image's depth, so the clouds really are ragged
+    model.opt.directions, model.opt.num_split, model.opt.sequential_outpainting = ["S"], 1, False
+    try:
+        B = 2
+        batch = make_batch(B, "identity")
+        batch["images"][0] = synthetic.synth_image(B, 3)           # two different images
+        g = torch.Generator().manual_seed(11)
+        noise, uniforms = torch.randn(16, B, 20, generator=g), torch.rand(B, 1024, generator=g)
+        _, out = model.forward(batch, noise=noise, uniforms=uniforms)
+        torch.cuda.synchronize()
+        scene_b = model.last_scene
+        keys = [k for k in out if k.startswith(("PredImg_", "FeaturesImg_"))]
+        assert len(keys) == 2 * len(scene_b) == 6 and all(out[k].shape[0] == B for k in keys)
+        n_bg = [int(s["background_mask"][b].sum()) for s in scene_b[:1] for b in range(B)]
+        assert n_bg[0] != n_bg[1]                                    # really ragged
+        # every view appends max-over-images(newly outpainted pixels) columns (shorter images are zero-padded)
+        grown = sum(max(int(s["background_mask"][b].sum()) for b in range(B)) for s in scene_b[:-1])
+        assert scene_b[-1]["cloud"].shape[2] == 256 * 256 + grown
+        for b in range(B):
+            one = {"images": [t[b:b + 1] for t in batch["images"]],
+                   "cameras": [{k: v[b:b + 1] for k, v in c.items()} for c in batch["cameras"]]}
+            _, o1 = model.forward(one, noise=noise[:, b:b + 1], uniforms=uniforms[b:b + 1])
+            torch.cuda.synchronize()
+            for k in keys:
+                if k.startswith("FeaturesImg_"):
+                    assert torch.equal(out[k][b], o1[k][0]), (k, b)
+                else:
+                    assert (out[k][b] - o1[k][0]).abs().max().item() <= 1e-5, (k, b)
+    finally:
+        model.opt.model_setting = "gen_paired_img"

@@ -159,9 +159,22 @@ int ps_conv_igemm(const ps_conv_desc* desc, void* stream);
 int ps_nchw_to_nhwc_bf16(const float* x, int N, int C, int H, int W, const uint8_t* mask, void* out, int cstride,
                          void* stream);
 /* NHWC bf16 resampling with up to two outputs y = act(v*scale+shift): mode 0 identity, 1 nn.AvgPool2d(3,2,1)
- * (blocks.py:46), 2 nn.Upsample(scale_factor=2, mode="bilinear") (blocks.py:48, architectures.py:201). */
+ * (blocks.py:46), 2 nn.Upsample(scale_factor=2, mode="bilinear") (blocks.py:48, architectures.py:201),
+ * 3 F.avg_pool2d(3, 2, 1, count_include_pad=False) (MultiscaleDiscriminator.downsample, discriminators.py:170-177),
+ * 4 nn.MaxPool2d(3, 2, 1) (torchvision resnet18, the places365 classifier of z_buffermodel.py:88). */
 int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int mode, const ps_conv_output* out0,
                 const ps_conv_output* out1, void* stream);
+/* nn.InstanceNorm2d(affine=False) of the discriminator (normalization.py:78-79) as a per-sample affine: statistics of
+ * x (N,HW,cstride) NHWC bf16 per (sample, channel), biased variance -> scale = rsqrt(var+eps), shift = -mean*scale, (N,C). */
+int ps_instance_norm_stats(const void* x, int N, int HW, int C, int cstride, float eps, float* scale, float* shift,
+                           void* stream);
+/* The places365 classifier's input exactly as get_best_sample builds it (z_buffermodel.py:105-110,256-257): image 0 of
+ * each of M candidates (f32, img_stride floats apart; (3,256,256) reshaped -- not permuted -- to (256,256,3)), uint8
+ * truncation, PIL antialiased bilinear 256->224 bit for bit (tap0[224] first tap, kk[224][4] 22-bit fixed-point weights,
+ * built by the host as Pillow's precompute_coeffs does; horizontal then vertical pass, each rounded to uint8), /255,
+ * ImageNet normalisation -> (M,224,224,8) NHWC bf16. */
+int ps_classifier_input(const float* img, long long img_stride, int M, const int* tap0, const int* kk, void* out,
+                        void* stream);
 /* LinearNoiseLayer + bn in eval mode (normalization.py:39-47,146-171): per-sample scale/shift (N,cpad) such that
  * bn(x, gain, bias) = x*scale + shift, from noise z (N,Z) and the spectrally normalised (C,Z) gain/bias matrices. */
 int ps_noise_affine(const float* z, int N, int Z, const float* Wg, const float* Wb, const float* mean, const float* var,

@@ -136,3 +136,76 @@ def vqvae_decode_code(sd, ids):
     h = F.relu(_vq_resblock(sd, "dec.blocks.2.", h))
     h = F.relu(F.conv_transpose2d(h, sd["dec.blocks.4.weight"], sd["dec.blocks.4.bias"], stride=2, padding=1))
     return F.conv_transpose2d(h, sd["dec.blocks.6.weight"], sd["dec.blocks.6.bias"], stride=2, padding=1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sample ranking networks: the multiscale PatchGAN discriminator and the places365 classifier
+# ---------------------------------------------------------------------------------------------------------------
+def _instance_norm(x, eps=1e-5):
+    return F.instance_norm(x, eps=eps)
+
+
+def discriminator_forward(sd, x):
+    """MultiscaleDiscriminator.forward (models/networks/discriminators.py:196-207) of two NLayerDiscriminators
+    (:78-140: n_layers_D = 4, ndf = 64, norm_D = spectralinstance, kernel 4, padding 2): returns the LAST feature map
+    of each scale -- all that D_Fake reads (models/losses/gan_loss.py:104-116).  The second scale sees
+    avg_pool2d(3, 2, 1, count_include_pad=False) of the input (:170-177)."""
+    outs = []
+    for d in range(2):
+        p = f"discriminator_{d}."
+        h = F.leaky_relu(F.conv2d(x, sd[p + "model0.0.weight"], sd[p + "model0.0.bias"], stride=2, padding=2), 0.2)
+        for n, stride in ((1, 2), (2, 2), (3, 1)):
+            h = F.conv2d(h, sn_weight(sd, p + f"model{n}.0.0."), None, stride=stride, padding=2)  # bias removed (normalization.py:69-73)
+            h = F.leaky_relu(_instance_norm(h), 0.2)
+        outs.append(F.conv2d(h, sd[p + "model4.0.weight"], sd[p + "model4.0.bias"], stride=1, padding=2))
+        x = F.avg_pool2d(x, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
+    return outs
+
+
+def d_fake(preds):
+    """D_Fake (gan_loss.py:172-181 -> GANLoss.__call__ :101-116 -> hinge, fake, for the discriminator :80-88):
+    mean over scales of -mean(min(-x - 1, 0)) over the whole fake batch."""
+    return sum(-torch.mean(torch.min(-x - 1, torch.zeros_like(x))) for x in preds) / len(preds)
+
+
+def classifier_input(gen_img0):
+    """z_buffermodel.py:256-257 with :105-110: the (3,256,256) image is RESHAPED (not permuted) to (256,256,3) --
+    a reinterpretation of the CHW buffer as HWC, which scrambles it; the reference does exactly this -- scaled to
+    uint8 (truncation), resized to 224x224 with PIL's antialiased bilinear filter, divided by 255 and normalised with
+    the ImageNet statistics.  PIL is test infrastructure here; the product restates the filter (csrc/elementwise.cu)."""
+    import numpy as np
+    from PIL import Image
+
+    a = ((gen_img0.detach().cpu().reshape(256, 256, 3).numpy() * .5 + .5) * 255).astype(np.uint8)
+    im = Image.fromarray(a).resize((224, 224), Image.BILINEAR)
+    t = torch.from_numpy(np.asarray(im).astype(np.float32) / 255.0).permute(2, 0, 1)
+    mean, std = torch.tensor([0.485, 0.456, 0.406]), torch.tensor([0.229, 0.224, 0.225])
+    return ((t - mean[:, None, None]) / std[:, None, None]).unsqueeze(0)
+
+
+def _bn(sd, p, x, eps=1e-5):
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, eps)
+
+
+def resnet18_logits(sd, x):
+    """torchvision.models.resnet18(num_classes=365).forward in eval mode (the classifier of z_buffermodel.py:88,258)."""
+    h = F.relu(_bn(sd, "bn1.", F.conv2d(x, sd["conv1.weight"], None, stride=2, padding=3)))
+    h = F.max_pool2d(h, 3, 2, 1)
+    for layer, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+        for blk in range(2):
+            p = f"layer{layer}.{blk}."
+            s = stride if blk == 0 else 1
+            idt = h
+            o = F.relu(_bn(sd, p + "bn1.", F.conv2d(h, sd[p + "conv1.weight"], None, stride=s, padding=1)))
+            o = _bn(sd, p + "bn2.", F.conv2d(o, sd[p + "conv2.weight"], None, padding=1))
+            if (p + "downsample.0.weight") in sd:
+                idt = _bn(sd, p + "downsample.1.", F.conv2d(h, sd[p + "downsample.0.weight"], None, stride=s))
+            h = F.relu(o + idt)
+    h = F.adaptive_avg_pool2d(h, 1).flatten(1)
+    return F.linear(h, sd["fc.weight"], sd["fc.bias"])
+
+
+def entropy(logits):
+    """-sum p log p of softmax(logits) per row (z_buffermodel.py:259-261)."""
+    p = torch.softmax(logits.double(), 1)
+    return -(p * torch.log(p)).sum(1)

@@ -30,6 +30,8 @@ SIGNATURES = {
     "ps_conv_igemm": (c_i, [c_p, c_p]),
     "ps_nchw_to_nhwc_bf16": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p]),
     "ps_resample": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "ps_instance_norm_stats": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
+    "ps_classifier_input": (c_i, [c_p, ctypes.c_longlong, c_i, c_p, c_p, c_p, c_p]),
     "ps_noise_affine": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_i, c_p, c_p, c_p]),
     "ps_vq_argmin": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p]),
     "ps_embed_codes": (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p]),

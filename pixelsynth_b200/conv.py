@@ -67,7 +67,8 @@ class PackedConv:
     def __init__(self, weight_taps, taps, bias=None, device="cuda"):
         cout, cin = weight_taps[0].shape
         self.Cout, self.Cin = cout, cin
-        self.cout_pad = round_up(cout, 16)
+        # the kernel takes the whole padded Cout as one UMMA N when it fits (<= 256), else 128-wide column blocks
+        self.cout_pad = round_up(cout, 16) if cout <= 256 else round_up(cout, 128)
         self.cin_pad = round_up(cin, 64)
         self.taps = list(taps)
         T = len(taps)

@@ -48,7 +48,9 @@ struct ResampleOut {
   int per_sample, act, cstride, coffset;
 };
 
-// mode 0: identity, 1: AvgPool2d(3, stride 2, pad 1, count_include_pad), 2: bilinear x2 (align_corners=False).
+// mode 0: identity, 1: AvgPool2d(3, stride 2, pad 1, count_include_pad), 2: bilinear x2 (align_corners=False),
+// 3: avg_pool2d(3, 2, 1, count_include_pad=False) (the discriminator's downsample, discriminators.py:170-177),
+// 4: MaxPool2d(3, 2, 1) (torchvision resnet18).
 // One thread per (output pixel, 8-channel group); up to two outputs y = act(v * scale + shift).
 __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __restrict__ in, int N, int H, int W, int C,
                                                        int in_cstride, int mode, int Ho, int Wo, ResampleOut o0,
@@ -79,6 +81,34 @@ __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __re
       for (int dx = -1; dx <= 1; ++dx) {
         const int y = 2 * oy + dy, x = 2 * ox + dx;
         if (y >= 0 && y < H && x >= 0 && x < W) accum(y, x, 1.0f / 9.0f);
+      }
+  } else if (mode == 3) {
+    int cnt = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int y = 2 * oy + dy, x = 2 * ox + dx;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+          accum(y, x, 1.0f);
+          ++cnt;
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] /= (float)cnt;
+  } else if (mode == 4) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = -INFINITY;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int y = 2 * oy + dy, x = 2 * ox + dx;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * H + y) * W + x) * in_cstride + g * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          v[2 * j] = fmaxf(v[2 * j], f.x);
+          v[2 * j + 1] = fmaxf(v[2 * j + 1], f.y);
+        }
       }
   } else {
     // PyTorch upsample_bilinear2d, align_corners=False: src = (dst + 0.5) / 2 - 0.5 clamped at 0
@@ -221,6 +251,104 @@ __global__ void tanh_residual_kernel(const float* __restrict__ v, const float* _
   out[idx] = before ? tanhf(v[idx]) + x[idx] : tanhf(v[idx] + x[idx]);
 }
 
+
+// InstanceNorm2d(affine=False) statistics of an NHWC bf16 tensor (the discriminator's norm layer,
+// normalization.py:78-79): per (sample, channel) over the H*W pixels, biased variance;
+// scale = rsqrt(var + eps), shift = -mean * scale, so that y = x * scale + shift.  grid (C/8, N), 256 threads.
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int cstride,
+                                                             float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * cstride + g * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      s[2 * j] += f.x;
+      s[2 * j + 1] += f.y;
+      q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+      q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+    }
+  }
+  __shared__ float red[2][8][8];  // [sum | sumsq][warp][channel]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+    }
+    if (lane == 0) {
+      red[0][warp][j] = s[j];
+      red[1][warp][j] = q[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int j = threadIdx.x;
+    float ts = 0.f, tq = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      ts += red[0][w][j];
+      tq += red[1][w][j];
+    }
+    const float mean = ts / (float)HW;
+    const float var = fmaxf(tq / (float)HW - mean * mean, 0.f);
+    const float r = rsqrtf(var + eps);
+    const int c = g * 8 + j;
+    if (c < C) {
+      scale[(size_t)n * C + c] = r;
+      shift[(size_t)n * C + c] = -mean * r;
+    }
+  }
+}
+
+// The classifier's input as the reference builds it (z_buffermodel.py:105-110,256-257): the candidate's image 0, a
+// (3,256,256) f32 buffer, is REINTERPRETED as (256,256,3) (reshape, not permute), scaled to uint8 by truncation, resized
+// to 224x224 with PIL's antialiased bilinear filter, divided by 255 and normalised with the ImageNet statistics.
+// The filter is Pillow's 8-bit path bit for bit: coefficients in 22-bit fixed point (tap0[224] first tap, kk[224][4]
+// integer weights, built on the host like precompute_coeffs / normalize_coeffs_8bpc), horizontal pass then vertical
+// pass, each (2^21 + sum kk * p) >> 22 clipped to uint8.  -> NHWC bf16 (M,224,224,8), channels 3..7 zero.
+__global__ void __launch_bounds__(256) classifier_input_kernel(const float* __restrict__ img, long long img_stride, int M,
+                                                               const int* __restrict__ tap0, const int* __restrict__ kk,
+                                                               __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * 224 * 224) return;
+  const int ox = idx % 224, oy = (idx / 224) % 224, m = idx / (224 * 224);
+  const float* src = img + (size_t)m * img_stride;
+  const int x0 = tap0[ox], y0 = tap0[oy];
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int ky = 0; ky < 4; ++ky) {
+    const int wy = kk[oy * 4 + ky];
+    if (wy == 0) continue;
+    const int y = y0 + ky;
+    int h[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int kx = 0; kx < 4; ++kx) {
+      const int wx = kk[ox * 4 + kx];
+      if (wx == 0) continue;
+      const float* px = src + ((size_t)y * 256 + (x0 + kx)) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int u8 = (int)fminf(fmaxf((px[c] * .5f + .5f) * 255.f, 0.f), 255.f);  // astype(np.uint8): truncation
+        h[c] += wx * u8;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += wy * min(max(h[c] >> 22, 0), 255);
+  }
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+  __nv_bfloat16 o[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] = __float2bfloat16(0.f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float u8 = (float)min(max(acc[c] >> 22, 0), 255);
+    o[c] = __float2bfloat16((u8 / 255.f - mean[c]) / sd[c]);
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
 }  // namespace ps
 
 using namespace ps;
@@ -241,9 +369,10 @@ int ps_nchw_to_nhwc_bf16(const float* x, int N, int C, int H, int W, const uint8
 int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int mode, const ps_conv_output* out0,
                 const ps_conv_output* out1, void* stream) {
   PS_CHECK_ARG(in && out0 && N >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && in_cstride % 8 == 0);
-  PS_CHECK_ARG(mode >= 0 && mode <= 2 && N <= 65535 && H <= 32767);
-  const int Ho = mode == 1 ? (H + 1) / 2 : (mode == 2 ? 2 * H : H);
-  const int Wo = mode == 1 ? (W + 1) / 2 : (mode == 2 ? 2 * W : W);
+  PS_CHECK_ARG(mode >= 0 && mode <= 4 && N <= 65535 && H <= 32767);
+  const bool half = mode == 1 || mode == 3 || mode == 4;
+  const int Ho = half ? (H + 1) / 2 : (mode == 2 ? 2 * H : H);
+  const int Wo = half ? (W + 1) / 2 : (mode == 2 ? 2 * W : W);
   ResampleOut o[2];
   memset(o, 0, sizeof(o));
   const ps_conv_output* src[2] = {out0, out1};
@@ -264,6 +393,27 @@ int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int 
   dim3 grid((unsigned)(((size_t)Wo * (C / 8) + 255) / 256), (unsigned)Ho, (unsigned)N);
   resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)in, N, H, W, C, in_cstride, mode, Ho, Wo, o[0], o[1]);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_instance_norm_stats(const void* x, int N, int HW, int C, int cstride, float eps, float* scale, float* shift,
+                           void* stream) {
+  PS_CHECK_ARG(x && scale && shift && N >= 0 && HW >= 1 && C >= 1 && cstride >= C && cstride % 8 == 0 && N <= 65535);
+  if (N == 0) return PS_OK;
+  instnorm_stats_kernel<<<dim3((unsigned)((C + 7) / 8), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, HW, C, cstride, eps, scale, shift);
+  PS_LAUNCHED();
+  return PS_OK;
+}
+
+int ps_classifier_input(const float* img, long long img_stride, int M, const int* tap0, const int* kk, void* out,
+                        void* stream) {
+  PS_CHECK_ARG(img && tap0 && kk && out && M >= 0 && img_stride >= 3 * 256 * 256);
+  if (M == 0) return PS_OK;
+  const int total = M * 224 * 224;
+  classifier_input_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(img, img_stride, M, tap0, kk,
+                                                                               (__nv_bfloat16*)out);
   PS_LAUNCHED();
   return PS_OK;
 }

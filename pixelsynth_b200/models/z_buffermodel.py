@@ -74,6 +74,7 @@ class ZbufferModelPts(nn.Module):
                      "outpaint2.": synthetic.make_state("lmconv", seed), "projector.": synthetic.make_state("decoder", seed)}
             state_dict = {p + k: v for p, sd in parts.items() for k, v in sd.items()}
         sd = strip_parallel_prefixes(state_dict)
+        self._state, self._seed = sd, seed
         self.pts_regressor = nets.UnetB200(_sub(sd, "pts_regressor."), device)
         self.pts_transformer = PtsManipulator(_get(opt, "W", 256), C=3, opt=opt).to(device)
         self.vqvae = nets.VQVAETopB200(_sub(sd, "vqvae."), device)
@@ -150,21 +151,46 @@ class ZbufferModelPts(nn.Module):
 
     def get_best_sample(self, order, words, sample_mask, codes, background_mask, gen_fs, netD, input_img, noise=None,
                         uniforms=None, prepared=None):
-        imgs = []
+        """z_buffermodel.py:244-276.  num_samples candidates are ONE sampler launch, one decode and one refinement pass
+        over a batch of num_samples * B images (candidate i = rows [i*B, (i+1)*B)); the reference loops over them.
+        uniforms: (B,n) shared by all candidates, or (num_samples,B,n); None = seeded per candidate like sample.py:14-16.
+        noise: (16,B,20) shared, (16,num_samples*B,20), or None = fresh draws like LinearNoiseLayer."""
         n = int(_get(self.opt, "num_samples", 1) or 1)
         B = codes.shape[0]
-        for i in range(n):
-            u = uniforms if uniforms is not None else self._sampler_uniforms(i, B)
-            sampled = self.outpaint2.sample(codes, order, words, sample_mask, u, float(_get(self.opt, "temperature", 1.0)),
-                                            prepared=prepared)
+        T = float(_get(self.opt, "temperature", 1.0))
+        if n == 1:
+            u = uniforms if uniforms is not None else self._sampler_uniforms(0, B)
+            sampled = self.outpaint2.sample(codes, order, words, sample_mask, u, T, prepared=prepared)
             ar_sample = self.vqvae.decode_code(sampled)
             combined = self.get_combined(gen_fs, ar_sample, background_mask)
-            imgs.append(self.projector.forward(combined, background_mask, noise))
-        if n == 1:
-            return imgs[0]
+            return self.projector.forward(combined, background_mask, noise)
+        if uniforms is None:
+            u = torch.cat([self._sampler_uniforms(i, B) for i in range(n)])
+        else:
+            u = torch.as_tensor(uniforms)
+            u = u.reshape(n * B, -1) if u.dim() == 3 else u.repeat(n, 1)
+        rep = lambda a: np.concatenate([np.asarray(a)] * n, 0)
+        sampled = self.outpaint2.sample(codes.repeat(n, 1, 1), rep(order), rep(words), rep(sample_mask), u, T)
+        ar_sample = self.vqvae.decode_code(sampled)
+        bg_n = background_mask.repeat(n, 1, 1)
+        combined = self.get_combined(gen_fs.repeat(n, 1, 1, 1), ar_sample, bg_n)
+        if noise is not None and noise.shape[1] == B:
+            noise = noise.repeat(1, n, 1)
+        imgs = self.projector.forward(combined, bg_n, noise).view(n, B, *gen_fs.shape[1:])
         if self.ranker is None:
-            return imgs[0]  # discriminator + classifier ranking (z_buffermodel.py:254-276) is a "next" row
-        return imgs[int(self.ranker(imgs, input_img))]
+            self.ranker = self._default_ranker()
+        best = int(self.ranker(imgs, input_img)) if self.ranker is not None else 0
+        self.last_best = best
+        return imgs[best]
+
+    def _default_ranker(self):
+        """The reference ranks with BaseModel.netD and ZbufferModelPts.classifier (demo.py:233-243 loads its places365
+        weights).  Built lazily from the state dict's `netD.` / `classifier.` entries, or seeded random when absent."""
+        from .. import ranking
+        sd = self._state
+        d = _sub(sd, "netD.netD.") or _sub(sd, "netD.") or synthetic.make_state("netD", self._seed)
+        c = _sub(sd, "classifier.") or synthetic.make_state("resnet18", self._seed)
+        return ranking.GpuRanker(nets.MultiscaleDiscriminatorB200(d, self.device), nets.ResNet18B200(c, self.device))
 
     # -- z_buffermodel.py:291-419 ---------------------------------------------------------------
     def forward_image(self, batch, netD=None, noise=None, uniforms=None):

@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import check
 from .conv import ConvOutput, Out, PackedConv, conv_igemm, round_up
 
-MODE = {"identity": 0, "avgpool": 1, "bilinear": 2}
+MODE = {"identity": 0, "avgpool": 1, "bilinear": 2, "avgpool_nopad": 3, "maxpool": 4}
 _ACT = {"none": 0, "relu": 1, "leaky": 2, "tanh": 3, "sigmoid_affine": 4, "elu": 5}
 
 
@@ -308,3 +308,171 @@ class ResNetDecoderB200:
         out = torch.empty_like(x)
         check(_lib.lib().ps_tanh_residual(_p(v32), _p(x), x.numel(), int(self.nbr), _p(out), _stream()), "ps_tanh_residual")
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sample ranking: ZbufferModelPts.get_best_sample scores every candidate with the multiscale PatchGAN's
+# D_Fake and with the entropy of a places365 resnet18 (models/z_buffermodel.py:244-276)
+# ---------------------------------------------------------------------------------------------------------------
+def pil_bilinear_table(in_size=256, out_size=224):
+    """First tap and the (at most three, stored as four) 22-bit fixed-point weights of PIL's antialiased bilinear resize
+    per output coordinate -- the filter torchvision's Resize applies to the PIL image at z_buffermodel.py:105-110.
+    Restates Pillow's precompute_coeffs + normalize_coeffs_8bpc (support = scale, triangle kernel, weights normalised
+    in double, rounded to (int)(0.5 + w * 2^22)); with these integers the device kernel reproduces PIL bit for bit
+    (tests/test_demo_cpu.py checks the table against PIL itself)."""
+    scale = in_size / out_size
+    fs = max(scale, 1.0)
+    support = 1.0 * fs
+    tap0, kk = [], []
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [max(0.0, 1.0 - abs((x + xmin - center + 0.5) / fs)) for x in range(xmax)]
+        tot = 0.0
+        for v in k:
+            tot += v
+        ki = [int(0.5 + v / tot * (1 << 22)) for v in k]
+        while ki and ki[-1] == 0:
+            ki.pop()
+        assert len(ki) <= 4, "PIL bilinear 256->224 never needs more than four taps"
+        tap0.append(xmin)
+        kk.append(ki + [0] * (4 - len(ki)))
+    return torch.tensor(tap0, dtype=torch.int32), torch.tensor(kk, dtype=torch.int32)
+
+
+class MultiscaleDiscriminatorB200:
+    """models/networks/discriminators.py:142-207 (two NLayerDiscriminators :78-140, n_layers_D 4, ndf 64, spectralinstance)
+    on conv_igemm_kernel; InstanceNorm2d = instnorm_stats_kernel + a per-sample affine fused with LeakyReLU in the
+    resampling kernel.  forward -> the last feature map of each scale (fp32), d_fake -> the D_Fake score per candidate."""
+
+    def __init__(self, sd, device="cuda"):
+        self.device = device
+        self.scales = []
+        for d in range(2):
+            p = f"discriminator_{d}."
+            first = PackedConv.conv2d(sd[p + "model0.0.weight"].float(), sd[p + "model0.0.bias"], padding=2, device=device)
+            mid = [PackedConv.conv2d(spectral_fold(sd, p + f"model{n}.0.0."), None, padding=2, device=device) for n in (1, 2, 3)]
+            last = PackedConv.conv2d(sd[p + "model4.0.weight"].float(), sd[p + "model4.0.bias"], padding=2, device=device)
+            self.scales.append((first, mid, last))
+
+    def _instnorm_leaky(self, raw):
+        n, h, w, c = raw.shape
+        scale = torch.empty((n, c), dtype=torch.float32, device=raw.device)
+        shift = torch.empty((n, c), dtype=torch.float32, device=raw.device)
+        check(_lib.lib().ps_instance_norm_stats(_p(raw), n, h * w, c, c, 1e-5, _p(scale), _p(shift), _stream()),
+              "ps_instance_norm_stats")
+        out = _buf(n, h, w, c, raw.device)
+        resample(raw, "identity", Out(out, "leaky", scale, shift, per_sample=True))
+        return out
+
+    def forward(self, x):
+        """x (M,3,S,S) f32 -> [ (M,1,h0,w0), (M,1,h1,w1) ] f32."""
+        m, _, S, _ = x.shape
+        dev = x.device
+        cur = nchw_to_nhwc(x, 8)
+        outs = []
+        for d, (first, mid, last) in enumerate(self.scales):
+            r = cur.shape[1]
+            o = r // 2 + 1                                           # kernel 4, stride 2, padding 2
+            h = _buf(m, o, o, 64, dev)
+            conv_igemm(cur, first, [Out(h, "leaky")], stride=2, Hout=o, Wout=o)
+            for pc, stride in zip(mid, (2, 2, 1)):
+                o = h.shape[1] // 2 + 1 if stride == 2 else h.shape[1] + 1
+                raw = _buf(m, o, o, pc.Cout, dev)
+                conv_igemm(h, pc, [Out(raw)], stride=stride, Hout=o, Wout=o)
+                h = self._instnorm_leaky(raw)
+            o = h.shape[1] + 1
+            y = torch.empty((m, 1, o, o), dtype=torch.float32, device=dev)
+            conv_igemm(h, last, [Out(None)], Hout=o, Wout=o, out_f32=y)
+            outs.append(y)
+            if d == 0:
+                nxt = _buf(m, (r + 1) // 2, (r + 1) // 2, 8, dev)
+                resample(cur, "avgpool_nopad", Out(nxt))
+                cur = nxt
+        return outs
+
+    def d_fake(self, x, groups):
+        """D_Fake (gan_loss.py:172-181, hinge) of `groups` candidates stacked along the batch: (groups,) f32."""
+        outs = self.forward(x)
+        per = [torch.relu(o.view(groups, -1) + 1).mean(1) for o in outs]      # -min(-x - 1, 0) = max(x + 1, 0)
+        return sum(per) / len(per)
+
+
+class ResNet18B200:
+    """torchvision.models.resnet18(num_classes=365) in eval mode (the places365 classifier, z_buffermodel.py:88,258) on
+    conv_igemm_kernel: batch norm folded into weights and bias, the 7x7 stem as two launches (49 taps > 32 per launch),
+    the strided 1x1 downsample convolutions as their own launches, the residual add + ReLU in the epilogue."""
+
+    def __init__(self, sd, device="cuda"):
+        self.device = device
+
+        def fold(conv, bn):
+            s = sd[bn + "weight"].float() / torch.sqrt(sd[bn + "running_var"].float() + 1e-5)
+            return sd[conv + "weight"].float() * s[:, None, None, None], sd[bn + "bias"].float() - sd[bn + "running_mean"].float() * s
+
+        w, b = fold("conv1.", "bn1.")
+        taps = [(ky - 3, kx - 3) for ky in range(7) for kx in range(7)]
+        wt = [w[:, :, ky, kx] for ky in range(7) for kx in range(7)]
+        self.stem_a = PackedConv(wt[:32], taps[:32], None, device)
+        self.stem_a.taps = taps[:16]
+        self.stem_b = PackedConv(wt[32:], taps[32:], b, device)
+        self.stem_b.taps = taps[32:48]
+        self.blocks = []
+        for layer, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+            for blk in range(2):
+                p = f"layer{layer}.{blk}."
+                w1, b1 = fold(p + "conv1.", p + "bn1.")
+                w2, b2 = fold(p + "conv2.", p + "bn2.")
+                ds = None
+                if (p + "downsample.0.weight") in sd:
+                    wd, bd = fold(p + "downsample.0.", p + "downsample.1.")
+                    ds = PackedConv.conv2d(wd, bd, padding=0, device=device)
+                self.blocks.append((stride if blk == 0 else 1, PackedConv.conv2d(w1, b1, padding=1, device=device),
+                                    PackedConv.conv2d(w2, b2, padding=1, device=device), ds))
+        self.fc = PackedConv.conv2d(sd["fc.weight"].float()[:, :, None, None], sd["fc.bias"], padding=0, device=device)
+        self.tap0, self.wtab = [t.to(device).contiguous() for t in pil_bilinear_table()]
+
+    def classifier_input(self, imgs):
+        """imgs (M,B,3,256,256) or (M,3,256,256) f32: image 0 of each candidate -> (M,224,224,8) NHWC bf16."""
+        imgs = imgs.contiguous().float()
+        m = imgs.shape[0]
+        stride = imgs[0].numel()
+        out = torch.empty((m, 224, 224, 8), dtype=torch.bfloat16, device=imgs.device)
+        check(_lib.lib().ps_classifier_input(_p(imgs), stride, m, _p(self.tap0), _p(self.wtab), _p(out), _stream()),
+              "ps_classifier_input")
+        return out
+
+    def logits_nhwc(self, x):
+        m = x.shape[0]
+        dev = x.device
+        a = _buf(m, 112, 112, 64, dev)
+        conv_igemm(x, self.stem_a, [Out(a)], stride=2, Hout=112, Wout=112, x2=x, pc2_taps=[(ky - 3, kx - 3) for ky in range(7)
+                   for kx in range(7)][16:32], pc2_wrow=self.stem_a.wrow[16:32])
+        h = _buf(m, 112, 112, 64, dev)
+        conv_igemm(x, self.stem_b, [Out(h, "relu")], stride=2, Hout=112, Wout=112, x2=x, pc2_taps=[(3, 3)],
+                   pc2_wrow=self.stem_b.wrow[16:17], residual=a)
+        p = _buf(m, 56, 56, 64, dev)
+        resample(h, "maxpool", Out(p))
+        h = p
+        for stride, c1, c2, ds in self.blocks:
+            r = h.shape[1] // stride
+            t = _buf(m, r, r, c1.Cout, dev)
+            conv_igemm(h, c1, [Out(t, "relu")], stride=stride, Hout=r, Wout=r)
+            idt = h
+            if ds is not None:
+                idt = _buf(m, r, r, ds.Cout, dev)
+                conv_igemm(h, ds, [Out(idt)], stride=stride, Hout=r, Wout=r)
+            o = _buf(m, r, r, c2.Cout, dev)
+            conv_igemm(t, c2, [Out(o, "relu")], residual=idt)
+            h = o
+        pooled = h.float().mean((1, 2)).to(torch.bfloat16).view(m, 1, 1, 512).contiguous()   # AdaptiveAvgPool2d(1)
+        out = torch.empty((m, 365, 1, 1), dtype=torch.float32, device=dev)
+        conv_igemm(pooled, self.fc, [Out(None)], out_f32=out)
+        return out.view(m, 365)
+
+    def entropy(self, imgs):
+        """-sum p log p of the class distribution of each candidate's image 0 (z_buffermodel.py:256-261): (M,) f64."""
+        lg = self.logits_nhwc(self.classifier_input(imgs)).double()
+        p = torch.softmax(lg, 1)
+        return -(p * torch.log(p)).sum(1)

@@ -6,9 +6,9 @@ The reference scores every candidate twice -- the discriminator's D_Fake loss on
 turns each score list into ranks and keeps the candidate with the largest
     0.5 * (n - 1 - entropy_rank) + 0.5 * discriminator_rank                                        (:264-276)
 i.e. low scene-classification entropy and high D_Fake.  The rank fusion is reproduced here exactly (host integers;
-pinned to the reference's own statements by tests/golden/make_demo_golden.py).  The two scoring networks are
-injected callables: their trained weights are not reachable offline (the classifier is fetched with wget at
-demo.py:222-226) and their forward passes are not on the sm_100a kernels yet (a "next" row).
+pinned to the reference's own statements by tests/golden/make_demo_golden.py).  GpuRanker scores ALL candidates in one
+batch on the sm_100a kernels (nets.MultiscaleDiscriminatorB200, nets.ResNet18B200) -- two device->host reads per call
+instead of the reference's two per candidate; Ranker keeps the injected-callable form.
 """
 import numpy as np
 import torch
@@ -59,3 +59,23 @@ class Ranker:
         d = [float(self.discriminator(im, input_img)) if self.discriminator else 0.0 for im in imgs]
         e = [entropy_of_logits(self.classifier(im[:1])) if self.classifier else 0.0 for im in imgs]   # image 0 only (:256)
         return rank_fusion(d, e)
+
+
+class GpuRanker:
+    """ranker(imgs (n,B,3,S,S), input_img) -> index of the best candidate, every score computed on the GPU in one batch:
+    D_Fake of the multiscale PatchGAN on each candidate's B images (gan_loss.py:172-181; the real half of the reference's
+    fake|real batch does not enter D_Fake and instance norm is per sample, so it is not run), and the entropy of the
+    places365 resnet18 on each candidate's image 0 through the reference's reshape + PIL resize (:256-261)."""
+
+    def __init__(self, discriminator, classifier):
+        self.discriminator = discriminator
+        self.classifier = classifier
+        self.last_scores = None
+
+    def __call__(self, imgs, input_img=None):
+        n, B = imgs.shape[:2]
+        d = self.discriminator.d_fake(imgs.reshape(n * B, *imgs.shape[2:]), n)
+        e = self.classifier.entropy(imgs)
+        d, e = d.float().cpu().numpy(), e.double().cpu().numpy()
+        self.last_scores = (d, e)
+        return rank_fusion(list(d), list(e))

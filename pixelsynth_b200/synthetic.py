@@ -93,6 +93,10 @@ def make_state(net, seed=0, gain=1.0):
         # a trained prior is peaked; with unit-scale logits over 512 classes every draw would sit on a near-uniform
         # CDF where a 1e-3 logit error already moves the token.  Sharpen the output layer (logit std ~6).
         sd["nin_out.lin_a.weight_g"] = sd["nin_out.lin_a.weight_g"] * 6.0
+    if net == "resnet18":
+        # a trained classifier's logits have unit-ish scale; with fan-in init through 18 layers they come out at std ~50
+        # and every softmax is one-hot (entropy 0 for every candidate, nothing to rank)
+        sd["fc.weight"] = sd["fc.weight"] * 0.04
     if net == "unet":
         # the depth head sees sigmoid(): widen its pre-activation (std ~1.5) so predicted depth really varies.
         # weight_orig / sigma is scale invariant, so the knob is the stored u vector (sigma = u . W v).

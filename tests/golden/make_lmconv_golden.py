@@ -16,6 +16,13 @@ sys.path.insert(0, "/root/reference")
 from oracle import lmconv_ref, weights  # noqa: E402
 
 
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+from _ref_import import use_reference_models  # noqa: E402
+
+use_reference_models()
+
 def install_stubs():
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors"):
         sys.modules.setdefault(name, types.ModuleType(name))

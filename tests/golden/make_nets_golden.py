@@ -16,6 +16,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 from oracle import nets_ref, weights  # noqa: E402
 
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+from _ref_import import use_reference_models  # noqa: E402
+
+use_reference_models()
+
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -86,6 +93,40 @@ def main():
         print("decoder max err", err, "pre-tanh saturation: frac |out|>0.99 =", (ref.abs() > 0.99).float().mean().item())
         assert err <= 1e-4
         fixture("decoder", ref)
+
+        # ---- sample ranking networks ----
+        from models.networks.discriminators import MultiscaleDiscriminator
+        import torchvision
+        od = Opt(ndf=64, norm_D="spectralinstance", output_nc=3, no_ganFeat_loss=False, isTrain=False)
+        sd = weights.make_state("netD", 0)
+        m = MultiscaleDiscriminator(od).eval()
+        m.load_state_dict(sd, strict=True)
+        xs = weights.synth_image(2, 4)
+        ref = m(xs)                                   # list (scale) of lists (layer outputs)
+        mine = nets_ref.discriminator_forward(sd, xs)
+        for r, o_ in zip(ref, mine):
+            err = (r[-1] - o_).abs().max().item()
+            print("netD last map", tuple(o_.shape), "max err", err, "std", r[-1].std().item())
+            assert err <= 1e-4 * max(1.0, r[-1].abs().max().item())
+        # D_Fake through the reference's own GANLoss (gan_loss.py:101-116, hinge)
+        from models.losses.gan_loss import GANLoss
+        crit = GANLoss("hinge", tensor=torch.FloatTensor, opt=od)
+        dref = crit(ref, False, for_discriminator=True)
+        dmine = nets_ref.d_fake(mine)
+        print("D_Fake", float(dref), float(dmine))
+        assert abs(float(dref) - float(dmine)) <= 1e-5
+        fixture("netD", torch.cat([r[-1].reshape(-1) for r in ref]), d_fake=float(dref))
+
+        sd = weights.make_state("resnet18", 0)
+        m = torchvision.models.resnet18(num_classes=365).eval()
+        m.load_state_dict(sd, strict=True)
+        xc = nets_ref.classifier_input(xs[0])
+        ref = m(xc)
+        mine = nets_ref.resnet18_logits(sd, xc)
+        err = (ref - mine).abs().max().item()
+        print("resnet18 logits max err", err, "std", ref.std().item(), "entropy", float(nets_ref.entropy(ref)))
+        assert err <= 1e-4 * max(1.0, ref.abs().max().item())
+        fixture("resnet18", ref, entropy=float(nets_ref.entropy(ref)))
 
 
 if __name__ == "__main__":

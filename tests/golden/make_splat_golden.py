@@ -23,6 +23,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import splat_ref  # noqa: E402
 
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+from _ref_import import use_reference_models  # noqa: E402
+
+use_reference_models()
+
 REF = "/root/reference"
 CAPTURE = {}
 

@@ -12,6 +12,13 @@ sys.path.insert(0, "/root/reference")
 sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
 
 
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+from _ref_import import use_reference_models  # noqa: E402
+
+use_reference_models()
+
 class Opt(dict):
     __getattr__ = dict.get
 
@@ -32,6 +39,11 @@ def main():
                               max_dilation=2, weight_norm=False, feature_norm_op=lambda c: PONO(), dropout_prob=0,
                               conv_bias=True, conv_mask_weight=False, rematerialize=False, binarize=False),  # :62-74
     }
+    import torchvision
+    from models.networks.discriminators import MultiscaleDiscriminator
+    od = Opt(ndf=64, norm_D="spectralinstance", output_nc=3, no_ganFeat_loss=False, isTrain=False)
+    nets["netD"] = MultiscaleDiscriminator(od)                                         # gan_loss.py:125-127, discriminators.py:142
+    nets["resnet18"] = torchvision.models.resnet18(num_classes=365)                    # z_buffermodel.py:88 (places365 classifier)
     out = {k: {n: [list(t.shape), str(t.dtype).replace("torch.", "")] for n, t in m.state_dict().items()}
            for k, m in nets.items()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "pixelsynth_b200", "data", "state_shapes.json")

@@ -208,3 +208,21 @@ def test_ragged_cloud_compaction_pads_with_zero_points():
     sel2 = torch.tensor([[1, 0, 1, 0, 0, 0], [0, 1, 0, 0, 0, 1]], dtype=torch.bool)
     ref = x[sel2.unsqueeze(1).repeat(1, 3, 1)].view(2, 3, -1)
     assert torch.equal(PtsManipulator._compact(sel2, x), ref)
+
+
+def test_pil_resize_table_reproduces_pil_bit_for_bit():
+    """The classifier's input is resized by PIL (z_buffermodel.py:105-110).  The product's integer filter table
+    (nets.pil_bilinear_table, consumed by classifier_input_kernel) applied the way the kernel applies it -- horizontal
+    pass, vertical pass, (2^21 + sum kk p) >> 22 clipped to uint8 -- equals PIL's own resize exactly."""
+    from PIL import Image
+    from pixelsynth_b200.nets import pil_bilinear_table
+
+    t0, kk = [t.numpy().astype(np.int64) for t in pil_bilinear_table()]
+    a = np.random.default_rng(3).integers(0, 256, (256, 256, 3)).astype(np.uint8)
+    ref = np.asarray(Image.fromarray(a).resize((224, 224), Image.BILINEAR)).astype(np.int64)
+    x = a.astype(np.int64)
+    h = np.stack([np.clip(((1 << 21) + sum(kk[ox, k] * x[:, t0[ox] + k] for k in range(4) if kk[ox, k])) >> 22, 0, 255)
+                  for ox in range(224)], 1)
+    v = np.stack([np.clip(((1 << 21) + sum(kk[oy, k] * h[t0[oy] + k] for k in range(4) if kk[oy, k])) >> 22, 0, 255)
+                  for oy in range(224)], 0)
+    assert np.array_equal(v, ref)

@@ -90,3 +90,47 @@ def test_refinement_decoder(env, nbr):
     # 16 bf16 convolutions + tanh: image within 0.06 abs everywhere, 0.01 rms
     assert err.max().item() <= 0.06
     assert err.pow(2).mean().sqrt().item() <= 0.01
+
+
+def test_discriminator_d_fake(env):
+    """MultiscaleDiscriminator on the conv kernel (instance norm as a per-sample affine).  Last feature maps
+    within 3% rms of the oracle's (five bf16 layers with a normalisation in between), D_Fake per candidate within 2%."""
+    nets_ref, weights, nets = env
+    sd = weights.make_state("netD", 0)
+    x = weights.synth_image(4, 7)
+    with torch.no_grad():
+        ref = nets_ref.discriminator_forward(sd, x)
+    D = nets.MultiscaleDiscriminatorB200(sd)
+    out = [o.cpu() for o in D.forward(x.cuda())]
+    assert [tuple(o.shape) for o in out] == [(4, 1, 35, 35), (4, 1, 19, 19)]
+    for o, r in zip(out, ref):
+        mx, rms = rel_err(o, r)
+        print("netD last map %s: max rel err %.4f rms rel err %.4f" % (tuple(o.shape), mx, rms))
+        assert rms <= 3e-2
+    got = D.d_fake(x.cuda(), 2).cpu()                       # two candidates of two images each
+    want = torch.stack([nets_ref.d_fake([r[:2] for r in ref]), nets_ref.d_fake([r[2:] for r in ref])])
+    print("D_Fake", got.tolist(), want.tolist())
+    assert torch.allclose(got, want, rtol=2e-2, atol=1e-3)
+
+
+def test_classifier_input_and_entropy(env):
+    """The places365 classifier path of get_best_sample: the reference's reshape + uint8 + PIL resize + normalise, bit for
+    bit up to the bf16 rounding of the normalised value; resnet18 logits within 2% rms; entropy within 0.03 nat."""
+    nets_ref, weights, nets = env
+    sd = weights.make_state("resnet18", 0)
+    imgs = weights.synth_image(3, 9)                        # three candidates, image 0 of each = the image itself
+    C = nets.ResNet18B200(sd)
+    xin = C.classifier_input(imgs.cuda().unsqueeze(1))      # (3,1,3,256,256) -> (3,224,224,8)
+    ref_in = torch.cat([nets_ref.classifier_input(im) for im in imgs])      # PIL on the CPU
+    got_in = xin[..., :3].permute(0, 3, 1, 2).float().cpu()
+    assert torch.equal(got_in, ref_in.to(torch.bfloat16).float())
+    assert (xin[..., 3:] == 0).all()
+    with torch.no_grad():
+        ref = nets_ref.resnet18_logits(sd, ref_in)
+    out = C.logits_nhwc(xin).cpu()
+    mx, rms = rel_err(out, ref)
+    print("resnet18 logits: max rel err %.4f rms rel err %.4f" % (mx, rms))
+    assert rms <= 2e-2
+    e, eref = C.entropy(imgs.cuda().unsqueeze(1)).cpu(), nets_ref.entropy(ref)
+    print("entropy", e.tolist(), eref.tolist())
+    assert torch.allclose(e, eref, atol=3e-2)

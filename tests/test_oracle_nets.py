@@ -33,7 +33,7 @@ def mods():
 
 def test_factory_is_deterministic_and_complete(mods):
     _, weights = mods
-    for net in ("unet", "decoder", "vqvae", "lmconv"):
+    for net in ("unet", "decoder", "vqvae", "lmconv", "netD", "resnet18"):
         a, b = weights.make_state(net, 0), weights.make_state(net, 0)
         assert list(a) == list(weights.shapes()[net])
         assert all(torch.equal(a[k], b[k]) for k in a)
@@ -69,3 +69,31 @@ def test_decoder_matches_reference_fixture(mods):
     noise = [torch.randn(1, 20, generator=g) for _ in range(16)]
     with torch.no_grad():
         check(nets_ref.decoder_forward(sd, xs, bg, noise), load("decoder"))
+
+
+def test_discriminator_matches_reference_fixture(mods):
+    """the multiscale PatchGAN's last feature maps and D_Fake, against the reference's own
+    MultiscaleDiscriminator + GANLoss run by make_nets_golden.py on the same seeded weights."""
+    nets_ref, weights = mods
+    sd = weights.make_state("netD", 0)
+    fx = load("netD")
+    with torch.no_grad():
+        outs = nets_ref.discriminator_forward(sd, weights.synth_image(2, 4))
+    assert [tuple(o.shape) for o in outs] == [(2, 1, 35, 35), (2, 1, 19, 19)]
+    check(torch.cat([o.reshape(-1) for o in outs]), fx)
+    assert abs(float(nets_ref.d_fake(outs)) - float(fx["d_fake"])) <= 1e-5
+
+
+def test_classifier_matches_torchvision_fixture(mods):
+    """The places365 classifier (torchvision resnet18, 365 classes) on the reference's scrambled, PIL-resized input
+    (z_buffermodel.py:256-261), and the entropy that ranks the candidates."""
+    nets_ref, weights = mods
+    sd = weights.make_state("resnet18", 0)
+    fx = load("resnet18")
+    with torch.no_grad():
+        xc = nets_ref.classifier_input(weights.synth_image(2, 4)[0])
+        assert tuple(xc.shape) == (1, 3, 224, 224)
+        out = nets_ref.resnet18_logits(sd, xc)
+    check(out, fx)
+    e = float(nets_ref.entropy(out))
+    assert abs(e - float(fx["entropy"])) <= 1e-4 and 1.0 < e < np.log(365)   # a distribution that can rank candidates

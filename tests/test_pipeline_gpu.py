@@ -265,3 +265,42 @@ def test_gen_scene_batched_equals_single(model):
                     assert (out[k][b] - o1[k][0]).abs().max().item() <= 1e-5, (k, b)
     finally:
         model.opt.model_setting = "gen_paired_img"
+
+
+def test_num_samples_ranking_matches_oracle_scores(oracle):
+    """z_buffermodel.py:244-276 with num_samples = 3: the candidates come out of ONE sampler launch / decode / refinement
+    batch, are scored on the GPU in one batch, and the GPU's scores and choice agree with the fp32 oracle's scorers run
+    on the same candidate images (discriminator D_Fake within 2%, entropy within 0.03 nat, same rank fusion)."""
+    from oracle import nets_ref
+    from pixelsynth_b200 import ranking, synthetic
+    from pixelsynth_b200.models.z_buffermodel import ZbufferModelPts
+
+    m = ZbufferModelPts(make_opt(num_samples=3))
+    B = 1
+    batch = make_batch(B)
+    g = torch.Generator().manual_seed(21)
+    uniforms = torch.rand(3, B, 1024, generator=g)           # a different draw per candidate
+    noise = torch.randn(16, 3 * B, 20, generator=g)
+    _, out = m.forward(batch, noise=noise, uniforms=uniforms)
+    torch.cuda.synchronize()
+    assert out["PredImg"].shape == (B, 3, 256, 256)
+    d, e = m.ranker.last_scores
+    assert len(d) == len(e) == 3 and len(set(np.round(d, 6))) == 3     # three different candidates
+    # the same candidates through the oracle's scorers
+    n = 3
+    m.opt.num_samples = 1
+    cands = []
+    for i in range(n):
+        _, o = m.forward(batch, noise=noise[:, i * B:(i + 1) * B], uniforms=uniforms[i])
+        cands.append(o["PredImg"].cpu())
+    sdD, sdC = synthetic.make_state("netD", 0), synthetic.make_state("resnet18", 0)
+    with torch.no_grad():
+        d_ref = [float(nets_ref.d_fake(nets_ref.discriminator_forward(sdD, c))) for c in cands]
+        e_ref = [float(nets_ref.entropy(nets_ref.resnet18_logits(sdC, nets_ref.classifier_input(c[0])))) for c in cands]
+    print("D_Fake gpu", d, "oracle", d_ref, "| entropy gpu", e, "oracle", e_ref)
+    np.testing.assert_allclose(d, d_ref, rtol=2e-2, atol=1e-3)
+    np.testing.assert_allclose(e, e_ref, atol=3e-2)
+    if min(abs(a - b) for i, a in enumerate(d_ref) for b in d_ref[i + 1:]) > 0.05 * max(d_ref) and \
+            min(abs(a - b) for i, a in enumerate(e_ref) for b in e_ref[i + 1:]) > 0.1:
+        assert m.last_best == ranking.rank_fusion(d_ref, e_ref)
+    assert torch.equal(out["PredImg"].cpu(), cands[m.last_best])     # the folded batch equals the per-candidate calls

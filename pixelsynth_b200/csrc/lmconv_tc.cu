@@ -71,6 +71,9 @@ constexpr int HALO_GROUP = 4;          // GEMMs per halo tile
 constexpr int CHAIN_ROWS = 32;         // rows of a chain tile
 constexpr int PART_ROW_BYTES = 640;    // one row's partial sums of one GEMM in shared memory (160 fp32)
 constexpr int PART_BUF_BYTES = CHAIN_ROWS * PART_ROW_BYTES;
+constexpr int XBUF_ROW_BYTES = 384;    // split epilogue: one row's next centre operand (192 fp16) in the exchange buffer
+constexpr int XBUF_BYTES = CHAIN_ROWS * XBUF_ROW_BYTES;
+constexpr int STAT_BYTES = 2 * 4 * CHAIN_ROWS * 8;  // split epilogue: per (parity, warp, row) a float2 of partial statistics
 
 enum { A_GATHER = 0, A_CENTRE = 1, A_EPILOGUE = 2, A_TMEM = 3, A_REUSE = 4 };
 
@@ -390,14 +393,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
   // and runs on into the stage's weight tile, which only feeds accumulator lanes nobody looks at.
   // A ring stage holds TWO consecutive chunks (slot = chunk & 1), so the issuer pays one barrier wait, one proxy
   // fence and one commit per eight MMAs.
-  const int a_rows = (tile.nrows + 7) & ~7;
+  // Chain tiles (<= 32 rows) run the "split" epilogue: the rows are REPLICATED in the four 32-lane TMEM quadrants (every
+  // A operand carries the 32 rows four times), and epilogue warp q computes channel groups q, q + 4, q + 8 of every row
+  // instead of one warp computing all 80 / 160 channels: four SM sub-partitions share the transcendental and issue
+  // work of the dependent chain.  PS_TC_DEBUG bit 15 keeps the one-thread-per-row epilogue.
+  const bool split_epi = is_chain && !(p.debug & 32768);
+  const int a_rows = split_epi ? 128 : (tile.nrows + 7) & ~7;
   const int a_bytes = a_rows * 128;
   const int slot_bytes = a_bytes + TC_W_BYTES;
   const int stage_bytes = 2 * slot_bytes;
   // a chain tile keeps two partial-sum buffers behind its (short) ring
-  const int ring_cap = TC_STAGES * TC_STAGE_BYTES - (is_chain ? 2 * PART_BUF_BYTES : 0);
+  const int ring_cap = TC_STAGES * TC_STAGE_BYTES - (is_chain ? 2 * PART_BUF_BYTES : 0) -
+                       (split_epi ? 2 * XBUF_BYTES + STAT_BYTES : 0);
   const int nst = min(TC_MAX_STAGES, ring_cap / stage_bytes);
   unsigned char* pbuf = tiles + ring_cap;
+  unsigned char* xbuf = pbuf + 2 * PART_BUF_BYTES;   // split epilogue only
+  unsigned char* statbuf = xbuf + 2 * XBUF_BYTES;
   // byte offset of chunk i's slot in the ring
   auto slot_off = [&](int i) { return ((i >> 1) % nst) * stage_bytes + (i & 1) * slot_bytes; };
 
@@ -550,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     // barrier wait, arrival) off the other three warps, which are busy with the next chunks.
     const int t = tid - 192;
     {
-      const ps_lmconv_row ri = sm.rows[t];
+      const ps_lmconv_row ri = sm.rows[split_epi ? (t & 31) : t];
       const bool v = (ri.w2_flags & ROW_VALID) != 0;
       const unsigned long long base =
           (unsigned long long)p.act +
@@ -563,7 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     const int gw = warp - 6, g = lane & 7, rs = lane >> 3;
     const uint32_t dst_even = smem_u32(tiles) + rs * 128 + ((g ^ rs) << 4);        // rows rs + 8m
     const uint32_t dst_odd = smem_u32(tiles) + (rs + 4) * 128 + ((g ^ (rs + 4)) << 4);  // rows rs + 4 + 8m
-    const int npair = (tile.nrows + 7) >> 3;  // row pairs (rs + 8m, rs + 4 + 8m) of this lane
+    const int npair = a_rows >> 3;  // row pairs (rs + 8m, rs + 4 + 8m) of this lane
     int seen = 0;                              // gathered chunks so far: this warp takes those with seen % 4 == gw
     int cur_gemm = -1;                         // chain tiles: GEMM whose partial sums were requested last
     unsigned int verified = tile.prev_count ? 0u : 0xffffffffu;  // progress every earlier level is known to have reached
@@ -659,7 +670,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     e.tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const ps_lmconv_row ri = sm.rows[r];
+    const ps_lmconv_row ri = sm.rows[split_epi ? lane : r];
     e.valid = (ri.w2_flags & ROW_VALID) != 0;
     const int b = ri.bc >> 10, cell = ri.bc & 1023;
     e.actrow = p.act + ((size_t)b * LMT_TENSORS * LMT_CELLS + cell) * LMT_ACT;
@@ -755,14 +766,322 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         tmem_st8_nowait(e.tlane + COL_A + 80, z);
         tmem_st8_nowait(e.tlane + COL_A + 88, z);
       }
+      const bool row_valid = e.valid;
+      if (split_epi && quad != 0) e.valid = false;  // the four replicas of a row compute the same u_init: one writes the cache
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
         tmem_st16_nowait(e.tlane + COL_OG + 16 * j, v + 16 * j);
         e.emit16(FORM_PAIR, j, v + 16 * j, 0, (p.raw_mask >> 0) & 1ull);
       }
+      e.valid = row_valid;
       e.publish();
       e.step_done();
     }
+
+    if (split_epi) {
+      // ================= split epilogue of a chain tile =================
+      // Warp `quad` owns channel groups (8 channels each) quad, quad + 4 and, for quad < 2, quad + 8 of all 32 rows; lane =
+      // row.  What needs a whole row -- the PONO statistics, the next centre operand (every replica lane needs all of it)
+      // -- goes through double-buffered shared memory and one named barrier of the four epilogue warps per exchange.
+      const int ng = quad < 2 ? 3 : 2;
+      float2* st2 = reinterpret_cast<float2*>(statbuf);
+      int sp = 0, xq = 0;  // parities of the statistics / operand exchange buffers
+      auto bar_epi = [] { asm volatile("bar.sync 2, 128;" ::: "memory"); };
+      const unsigned char* prow_l = pbuf + lane * PART_ROW_BYTES;
+      // x[8 i .. 8 i + 8) += 8 fp32 of GEMM gi's partial sums starting at column col8 * 8 (two 16-byte chunks)
+      auto part8 = [&](float* x, int gi, int col8) {
+        const unsigned char* b = prow_l + (gi & 1) * PART_BUF_BYTES;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 f = *reinterpret_cast<const float4*>(b + (((2 * col8 + h) ^ (lane & 7)) << 4));
+          x[4 * h] += f.x;
+          x[4 * h + 1] += f.y;
+          x[4 * h + 2] += f.z;
+          x[4 * h + 3] += f.w;
+        }
+      };
+      auto bias8 = [&](float* x, const float* bp) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(bp)), c = __ldg(reinterpret_cast<const float4*>(bp) + 1);
+        x[0] += a.x, x[1] += a.y, x[2] += a.z, x[3] += a.w, x[4] += c.x, x[5] += c.y, x[6] += c.z, x[7] += c.w;
+      };
+      // positional normalisation over the row's 80 channels, 24 or 16 of them here (layers.py:224-236, unbiased variance)
+      auto pono_split = [&](float* x) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (i < ng) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              s1 += x[8 * i + k];
+              s2 = fmaf(x[8 * i + k], x[8 * i + k], s2);
+            }
+          }
+        st2[(sp * 4 + quad) * 32 + lane] = make_float2(s1, s2);
+        bar_epi();
+        float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 tq = st2[(sp * 4 + q) * 32 + lane];
+          S1 += tq.x;
+          S2 += tq.y;
+        }
+        sp ^= 1;
+        const float mean = S1 * (1.0f / LMT_F);
+        const float inv = rsqrtf(fmaxf(S2 - S1 * mean, 0.f) * (1.0f / (LMT_F - 1)) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (i < ng) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[8 * i + k] = (x[8 * i + k] - mean) * inv;
+          }
+      };
+      // cache rows of this warp's channel groups + (form != NONE) the next GEMM's centre operand for every replica lane
+      auto emit_split = [&](int form, const float* x, int tensor, bool raw) {
+        uint4* crow = e.valid ? reinterpret_cast<uint4*>(e.actrow + (size_t)tensor * LMT_CELLS * LMT_ACT) : nullptr;
+        unsigned char* xrow = xbuf + xq * XBUF_BYTES + lane * XBUF_ROW_BYTES;
+        auto xchunk = [&](int c) { return reinterpret_cast<uint4*>(xrow + ((c ^ (lane & 7)) << 4)); };
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (i < ng) {
+            const int gr = quad + 4 * i;
+            uint32_t pp[4], nn[4], rr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float p0, n0, p1, n1;
+              celu(x[8 * i + 2 * k], p0, n0);
+              celu(x[8 * i + 2 * k + 1], p1, n1);
+              pp[k] = pack_h2(p0, p1);
+              nn[k] = pack_h2(n0, n1);
+              rr[k] = pack_h2(x[8 * i + 2 * k], x[8 * i + 2 * k + 1]);
+            }
+            if (crow) {
+              crow[gr] = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+              crow[10 + gr] = make_uint4(nn[0], nn[1], nn[2], nn[3]);
+              if (raw) crow[20 + gr] = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+            }
+            if (form == FORM_PAIR) {
+              *xchunk(gr) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+              *xchunk(10 + gr) = make_uint4(nn[0], nn[1], nn[2], nn[3]);
+            } else if (form == FORM_RAW) {
+              *xchunk(gr) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+            }
+          }
+        if (form == FORM_NONE) return;
+        bar_epi();
+        const int nchunk2 = form == FORM_PAIR ? 10 : 5;  // pairs of 16-byte chunks = 8 TMEM columns each
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+          if (j < nchunk2) {
+            const uint4 a = *xchunk(2 * j), c = *xchunk(2 * j + 1);
+            const uint32_t v8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+            tmem_st8_nowait(e.tlane + COL_A + 8 * j, v8);
+          }
+        if (form == FORM_RAW) {  // K = [x 0..79 | 0 .. 127]
+          const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int j = 0; j < 3; ++j) tmem_st8_nowait(e.tlane + COL_A + 40 + 8 * j, z);
+        }
+        xq ^= 1;
+      };
+
+      for (int oi = 0; oi < TC_NOPS; ++oi) {
+        const ps_lmconv_op op = p.ops[oi];
+        const int next_form = oi + 1 < TC_NOPS ? (p.ops[oi + 1].kind == 0 ? FORM_PAIR : FORM_RAW) : FORM_NONE;
+        const bool out_raw = (p.raw_mask >> op.out) & 1ull;
+        {  // first GEMM of the op: conv_input (+ nin_skip) of a gated resnet, or the dilated convolution
+          const uint32_t col0 = (uint32_t)(g & 1) * 160u;
+          mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
+          if (r == 0) TC_TRACE(4, g);
+          tc_fence_after();
+          float x[24];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < ng) tmem_ld8_nowait(e.tlane + col0 + 8 * (quad + 4 * i), x + 8 * i);
+          tmem_ld_wait();
+          mbar_wait(&sm.pfull[g & 1], (uint32_t)(g >> 1) & 1u);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < ng) {
+              bias8(x + 8 * i, bias + op.b_in + 8 * (quad + 4 * i));
+              part8(x + 8 * i, g, quad + 4 * i);
+            }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.pempty[g & 1]);
+          pono_split(x);
+          if (op.kind == 0) {
+            if (op.a >= 0) {
+              float sk[24];
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                if (i < ng) tmem_ld8_nowait(e.tlane + col0 + 80 + 8 * (quad + 4 * i), sk + 8 * i);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                if (i < ng) {
+                  bias8(sk + 8 * i, bias + op.b_skip + 8 * (quad + 4 * i));
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) x[8 * i + k] += sk[8 * i + k];
+                }
+            }
+            if (r == 0) TC_TRACE(6, g);
+            emit_split(FORM_PAIR, x, op.mid, false);
+            e.publish();
+          } else {  // the dilated convolution's PONO output becomes the new residual stream
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              if (i < ng) {
+                tmem_st8_nowait(e.tlane + COL_OG + 8 * (quad + 4 * i), reinterpret_cast<const uint32_t*>(x + 8 * i));
+              }
+            emit_split(next_form, x, op.out, out_raw);
+            if (next_form != FORM_NONE) e.publish(); else { tmem_st_wait(); tc_fence_before(); }
+          }
+          e.step_done();
+          if (r == 0) TC_TRACE(5, g);
+          ++g;
+        }
+        if (op.kind == 0) {  // y = conv_out(concat_elu(x)); og += PONO(y[:80]) * sigmoid(y[80:])
+          const uint32_t col0 = (uint32_t)(g & 1) * 160u;
+          mbar_wait(&sm.acc_full[g & 1], (uint32_t)(g >> 1) & 1u);
+          if (r == 0) TC_TRACE(4, g);
+          tc_fence_after();
+          float a[24], gt[24], o[24];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < ng) {
+              tmem_ld8_nowait(e.tlane + col0 + 8 * (quad + 4 * i), a + 8 * i);
+              tmem_ld8_nowait(e.tlane + col0 + 80 + 8 * (quad + 4 * i), gt + 8 * i);
+              tmem_ld8_nowait(e.tlane + COL_OG + 8 * (quad + 4 * i), o + 8 * i);
+            }
+          tmem_ld_wait();
+          mbar_wait(&sm.pfull[g & 1], (uint32_t)(g >> 1) & 1u);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < ng) {
+              bias8(a + 8 * i, bias + op.b_out + 8 * (quad + 4 * i));
+              part8(a + 8 * i, g, quad + 4 * i);
+              bias8(gt + 8 * i, bias + op.b_out + 80 + 8 * (quad + 4 * i));
+              part8(gt + 8 * i, g, 10 + quad + 4 * i);
+            }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.pempty[g & 1]);
+          pono_split(a);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < ng) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                o[8 * i + k] = fmaf(a[8 * i + k], __fdividef(1.0f, 1.0f + __expf(-gt[8 * i + k])), o[8 * i + k]);
+              tmem_st8_nowait(e.tlane + COL_OG + 8 * (quad + 4 * i), reinterpret_cast<const uint32_t*>(o + 8 * i));
+            }
+          emit_split(next_form, o, op.out, out_raw);
+          if (next_form != FORM_NONE) e.publish(); else { tmem_st_wait(); tc_fence_before(); }
+          e.step_done();
+          if (r == 0) TC_TRACE(5, g);
+          ++g;
+        }
+      }
+
+      if (need_logits) {
+        // ---- logits = nin_out(elu(u)): the operand A = [elu(u) | 0] of every replica row goes into quarter 0's ring slots
+        const int first = logit_first;
+        {
+          unsigned char* xrow = xbuf + xq * XBUF_BYTES + lane * XBUF_ROW_BYTES;
+          auto xchunk = [&](int c) { return reinterpret_cast<uint4*>(xrow + ((c ^ (lane & 7)) << 4)); };
+          float o[24];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < ng) tmem_ld8_nowait(e.tlane + COL_OG + 8 * (quad + 4 * i), o + 8 * i);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < ng) {
+              uint32_t pp[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float p0, n0, p1, n1;
+                celu(o[8 * i + 2 * k], p0, n0);
+                celu(o[8 * i + 2 * k + 1], p1, n1);
+                pp[k] = pack_h2(p0, p1);
+              }
+              *xchunk(quad + 4 * i) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+            }
+          bar_epi();
+#pragma unroll
+          for (int kg = 0; kg < 10; ++kg) sts_a(tiles, slot_off(first + (kg >> 3)), kg & 7, r, *xchunk(kg));
+#pragma unroll
+          for (int kg = 10; kg < 16; ++kg) sts_a(tiles, slot_off(first + 1), kg & 7, r, make_uint4(0, 0, 0, 0));
+          xq ^= 1;
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane < 8) {
+            mbar_arrive(&sm.full[(first >> 1) % nst]);
+            mbar_arrive(&sm.full[((first + 1) >> 1) % nst]);
+          }
+        }
+        mbar_wait(&sm.acc_full[2], 0);
+        tc_fence_after();
+        // ---- the draw, split over the warps: warp `quad` owns classes [128 quad, 128 quad + 128) of every row ----
+        const bool sampled = e.valid && (ri.w2_flags & ROW_SAMPLED) && p.uniforms;
+        const int cq = quad * 128;
+        float mx = -INFINITY, sum = 0.f;
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          float l[16];
+          tmem_ld16_nowait(e.tlane + cq + c0, l);
+          tmem_ld_wait();
+          float m2 = mx;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            l[i] = (l[i] + __ldg(bias + p.b_nin + cq + c0 + i)) * p.inv_temperature;
+            m2 = fmaxf(m2, l[i]);
+          }
+          sum *= __expf(mx - m2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sum += __expf(l[i] - m2);
+          mx = m2;
+        }
+        st2[(sp * 4 + quad) * 32 + lane] = make_float2(mx, sum);
+        bar_epi();
+        float M = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) M = fmaxf(M, st2[(sp * 4 + q) * 32 + lane].x);
+        float before = 0.f, mine = 0.f, total = 0.f;  // softmax mass of the quarters before this one / of this one / of all
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 tq = st2[(sp * 4 + q) * 32 + lane];
+          const float w = tq.y * __expf(tq.x - M);
+          if (q < quad) before += w;
+          if (q == quad) mine = w;
+          total += w;
+        }
+        sp ^= 1;
+        // token = first class whose cumulative mass exceeds u * total; the quarter that holds the crossing finds it
+        const float thr = sampled ? p.uniforms[(size_t)b * p.ustride + ri.uidx] * total : 0.f;
+        const bool claim = sampled && thr >= before && (quad == 3 || thr < before + mine);
+        if (__any_sync(0xffffffffu, claim)) {
+          float cum = before;
+          int token = cq + 127;
+          bool found = !claim;
+          for (int c0 = 0; c0 < 128; c0 += 16) {
+            if (__all_sync(0xffffffffu, found)) break;
+            float l[16];
+            tmem_ld16_nowait(e.tlane + cq + c0, l);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              cum += __expf((l[i] + __ldg(bias + p.b_nin + cq + c0 + i)) * p.inv_temperature - M);
+              if (!found && cum > thr) {
+                token = cq + c0 + i;
+                found = true;
+              }
+            }
+          }
+          if (claim) __stcg(p.codes + (size_t)b * LMT_CELLS + cell, (long long)token);
+        }
+        tc_fence_before();
+      }
+      e.step_done();  // progress PROG_DONE: the tile's tokens (if any) are in `codes`
+    } else {
 
     for (int oi = 0; oi < TC_NOPS; ++oi) {
       const ps_lmconv_op op = p.ops[oi];
@@ -945,6 +1264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
       tc_fence_before();
     }
     e.step_done();  // progress PROG_DONE: the tile's tokens (if any) are in `codes`
+    }  // !split_epi
     }  // !is_halo
   }
   __syncthreads();

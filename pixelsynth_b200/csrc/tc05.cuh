@@ -399,6 +399,13 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* f) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+// 8 columns, no wait
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* f) {
+  uint32_t* v = reinterpret_cast<uint32_t*>(f);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const float* f) {
   const uint32_t* v = reinterpret_cast<const uint32_t*>(f);

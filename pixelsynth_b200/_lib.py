@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpixelsynth_b200.so")
+LIB_PATH = os.environ.get("PS_LIB_PATH") or os.path.join(_HERE, "libpixelsynth_b200.so")  # PS_LIB_PATH: developer A/B builds
 
 c_f = ctypes.c_float
 c_d = ctypes.c_double

@@ -51,8 +51,14 @@ struct ConvKernelParams {
   int wrow[2][16];  // first weight row (of the packed [rows][Cin_pad] matrix) of each tap
   int BN;           // output channels per CTA (multiple of 16, <= 256)
   int stages;
-  int halo;         // 3x3 stride-1 mode: input 0's taps are read in place from one (TH+2) x 16-pixel halo tile per chunk
-  int a_stage_bytes;  // A part of a ring stage (0 when no k-iteration stages an A tile)
+  int halo;         // 3x3 stride-1 mode: every tap is read in place from one (TH+2) x (TW+2)-pixel halo tile per 64-channel chunk
+  int a_stage_bytes;  // A part of a ring stage (0 in halo mode: no k-iteration stages an A tile there)
+  // A CTA works on GROUPS of tpg (1 or 2) spatially adjacent tiles of one column block: a weight tile that has been
+  // brought into shared memory is multiplied against every tile of the group before it is released, so with tpg = 2 the
+  // weights -- 9 x 16 KB per 64 input channels, re-read for every tile, the kernel's largest L2 stream -- are read half as often.
+  int tpg, groups_per_cb, total_groups;
+  int nbuf;         // TMEM accumulator buffers (2 * tpg): the epilogue of one group overlaps the main loop of the next
+  int nhalo;        // halo buffers (2 * tpg)
   int debug;
   // epilogue
   int Cout;  // real output channels (columns >= Cout are dropped)
@@ -131,33 +137,42 @@ __device__ __forceinline__ void stage_block32(const float* f, const float4* sc, 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH,
-                      const ConvKernelParams p) {
+                      const __grid_constant__ CUtensorMap mapH1, const ConvKernelParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform to the compiler as well
   const int BN = p.BN;
   const int BNp = (BN + 31) & ~31;  // TMEM columns per accumulator buffer
   const int stage_bytes = p.a_stage_bytes + BN * BK * 2;
-  // carve: [2 halo tiles (halo mode)] [stages x (A | B)] then barriers
+  // carve: [nhalo halo tiles (halo mode)] [stages x (A | B)] then barriers
   unsigned char* halo_tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
-  unsigned char* tiles = halo_tiles + (p.halo ? 2 * HALO_BYTES : 0);
+  unsigned char* tiles = halo_tiles + (p.halo ? p.nhalo * HALO_BYTES : 0);
   uint64_t* full_bar = (uint64_t*)(tiles + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* acc_full = empty_bar + p.stages;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* halo_full = acc_empty + 2;
-  uint64_t* halo_empty = halo_full + 2;
-  uint32_t* tmem_slot = (uint32_t*)(halo_empty + 2);
+  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* halo_full = acc_empty + 4;
+  uint64_t* halo_empty = halo_full + 4;
+  uint32_t* tmem_slot = (uint32_t*)(halo_empty + 4);
   unsigned char* param_smem = (unsigned char*)(tmem_slot + 4);  // 16-byte aligned: 8 warps x 2 buffers x 40 float4
   unsigned char* stage_smem = param_smem + 8 * 2 * 40 * 16;      // 8 warps x 2 staging tiles of 2 KB
   const int kiters = p.ntaps[0] * p.kchunks[0] + p.ntaps[1] * p.kchunks[1];
-  const uint32_t ncols = 2 * BNp <= 32 ? 32u : (2 * BNp <= 64 ? 64u : (2 * BNp <= 128 ? 128u : (2 * BNp <= 256 ? 256u : 512u)));
+  const int acc_cols = p.nbuf * BNp;
+  const uint32_t ncols = acc_cols <= 32 ? 32u : (acc_cols <= 64 ? 64u : (acc_cols <= 128 ? 128u : (acc_cols <= 256 ? 256u : 512u)));
+  // nbuf = nhalo = 2 * tpg is 2 or 4: masks and shifts (a division by a run-time value leaves the uniform datapath,
+  // and everything derived from it would reach the MMA instructions through per-use R2UR moves)
+  const int tpg = p.tpg, bshift = tpg, bmask = 2 * tpg - 1;
+  // group gi -> column block, first spatial tile and number of tiles (the last group of a column block may hold one)
+  auto group_cb = [&](int gi) { return gi / p.groups_per_cb; };
+  auto group_sp0 = [&](int gi) { return (gi % p.groups_per_cb) * tpg; };
+  auto group_nt = [&](int gi) { return min(tpg, p.tiles_spatial - group_sp0(gi)); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapW);
     if (p.ntaps[1]) tma_prefetch_desc(&mapA1);
     if (p.halo) tma_prefetch_desc(&mapH);
+    if (p.halo && p.ntaps[1]) tma_prefetch_desc(&mapH1);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -165,7 +180,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < 4; ++b) {
         mbar_init(&acc_full[b], 1);
         mbar_init(&acc_empty[b], 8);  // one arrival per epilogue warp
         mbar_init(&halo_full[b], 1);
@@ -190,28 +205,32 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     const uint32_t w_bytes = (uint32_t)(BN * BK * 2);
     int s = 0, hit = 0;
     uint32_t ph = 1;  // parity of the `empty` phase to wait for (passes on a fresh barrier)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int sp = tile % p.tiles_spatial, cb = tile / p.tiles_spatial;
-      const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
-      const int ox0 = tx * p.TW, oy0 = ty * p.TH, n0 = tn * p.TN, ncol0 = cb * BN;
+    for (int gi = blockIdx.x; gi < p.total_groups; gi += gridDim.x) {
+      const int cb = group_cb(gi), sp0 = group_sp0(gi), nt = group_nt(gi), ncol0 = cb * BN;
       for (int src = 0; src < 2; ++src) {
-        const CUtensorMap* mA = src ? &mapA1 : &mapA0;
-        if (src == 0 && p.halo) {
-          // one halo tile per 64-channel chunk, then the nine weight tiles that are multiplied against it
-          for (int kc = 0; kc < p.kchunks[0]; ++kc, ++hit) {
-            const int hb = hit & 1;
-            mbar_wait(&halo_empty[hb], (((uint32_t)hit >> 1) & 1u) ^ 1u);
-            if (elect_one()) {
-              if (p.debug & 8) {
-                mbar_arrive(&halo_full[hb]);
-              } else {
-                mbar_expect_tx(&halo_full[hb], (uint32_t)HALO_LOAD_BYTES);
-                tma_load_4d(&mapH, &halo_full[hb], halo_tiles + (size_t)hb * HALO_BYTES, kc * BK, ox0 - 1, oy0 - 1, n0);
+        if (p.ntaps[src] == 0) continue;
+        if (p.halo) {
+          // per 64-channel chunk: one halo tile per tile of the group, then the weight tiles that are multiplied against them
+          const CUtensorMap* mH = src ? &mapH1 : &mapH;
+          for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+            for (int j = 0; j < nt; ++j, ++hit) {
+              const int sp = sp0 + j;
+              const int tx = sp % p.tiles_x, ty = (sp / p.tiles_x) % p.tiles_y, tn = sp / (p.tiles_x * p.tiles_y);
+              const int hb = hit & bmask;
+              mbar_wait(&halo_empty[hb], (((uint32_t)(hit >> bshift)) & 1u) ^ 1u);
+              if (elect_one()) {
+                if (p.debug & 8) {
+                  mbar_arrive(&halo_full[hb]);
+                } else {
+                  mbar_expect_tx(&halo_full[hb], (uint32_t)HALO_LOAD_BYTES);
+                  tma_load_4d(mH, &halo_full[hb], halo_tiles + (size_t)hb * HALO_BYTES, kc * BK, tx * p.TW - 1, ty * p.TH - 1,
+                              tn * p.TN);
+                }
               }
+              __syncwarp();
             }
-            __syncwarp();
-            for (int t = 0; t < p.ntaps[0]; ++t) {
-              const int wr = __shfl_sync(0xffffffffu, my_w0, t);
+            for (int t = 0; t < p.ntaps[src]; ++t) {
+              const int wr = __shfl_sync(0xffffffffu, src ? my_w1 : my_w0, t);
               mbar_wait(&empty_bar[s], ph);
               if (elect_one()) {
                 if (p.debug & 8) {
@@ -230,6 +249,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
           }
           continue;
         }
+        // tap mode (one tile per group): the tap's shifted window is fetched into the stage next to its weights
+        const CUtensorMap* mA = src ? &mapA1 : &mapA0;
+        const int tx = sp0 % p.tiles_x, ty = (sp0 / p.tiles_x) % p.tiles_y, tn = sp0 / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx * p.TW, oy0 = ty * p.TH, n0 = tn * p.TN;
         for (int t = 0; t < p.ntaps[src]; ++t) {
           const int dx = __shfl_sync(0xffffffffu, src ? my_dx1 : my_dx0, t);
           const int dy = __shfl_sync(0xffffffffu, src ? my_dy1 : my_dy0, t);
@@ -261,55 +284,77 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     // ===== MMA issuer: whole warp, warp-uniform operands, one elected lane issues (tc05.cuh: umma_f16_kblock) =====
     const uint32_t idesc = umma_idesc_bf16(BN);
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(tiles));
-    const int my_r0 = (1 + p.dy[0][lane & 15]) * HALO_W + 1 + p.dx[0][lane & 15];  // lane t: tap t's start row in the halo tile
+    // lane t: tap t's start row in the halo tile, for either input
+    const int my_r0 = (1 + p.dy[0][lane & 15]) * HALO_W + 1 + p.dx[0][lane & 15];
+    const int my_r1 = (1 + p.dy[1][lane & 15]) * HALO_W + 1 + p.dx[1][lane & 15];
     int s = 0, lt = 0, hit = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      mbar_wait(&acc_empty[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer
+    for (int gi = blockIdx.x; gi < p.total_groups; gi += gridDim.x) {
+      const int nt = group_nt(gi);
+      // scalars, not arrays: the MMA operands must stay warp-uniform registers (tc05.cuh, umma_f16_kblock)
+      const int buf0 = lt & bmask, buf1 = (lt + 1) & bmask;
+      mbar_wait(&acc_empty[buf0], (((uint32_t)(lt >> bshift)) & 1u) ^ 1u);  // the epilogue has drained this buffer
+      if (nt == 2) mbar_wait(&acc_empty[buf1], (((uint32_t)((lt + 1) >> bshift)) & 1u) ^ 1u);
+      // (the shuffles tell the compiler these are warp-uniform: they then live in uniform registers)
+      const uint32_t d0 = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(buf0 * BNp), 0);
+      const uint32_t d1 = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(buf1 * BNp), 0);
+      const uint32_t d_last = nt == 2 ? d1 : d0;
       tc_fence_after();
-      const uint32_t d = tmem_base + (uint32_t)(buf * BNp);
       int it = 0;
       if (p.halo) {
-        for (int kc = 0; kc < p.kchunks[0]; ++kc, ++hit) {
-          const int hb = hit & 1;
-          mbar_wait(&halo_full[hb], ((uint32_t)hit >> 1) & 1u);
-          tc_fence_after();
-          const uint32_t halo_addr = smem_u32(halo_tiles + (size_t)hb * HALO_BYTES);
-          for (int t = 0; t < p.ntaps[0]; ++t, ++it) {
-            mbar_wait(&full_bar[s], ph);
+        for (int src = 0; src < 2; ++src) {
+          for (int kc = 0; kc < (p.ntaps[src] ? p.kchunks[src] : 0); ++kc) {
+            const int hb0 = hit & bmask, hb1 = (hit + 1) & bmask;
+            mbar_wait(&halo_full[hb0], ((uint32_t)(hit >> bshift)) & 1u);
+            if (nt == 2) mbar_wait(&halo_full[hb1], ((uint32_t)((hit + 1) >> bshift)) & 1u);
+            hit += nt;
+            const uint32_t h0 = __shfl_sync(0xffffffffu, smem_u32(halo_tiles) + (uint32_t)(hb0 * HALO_BYTES), 0);
+            const uint32_t h1 = __shfl_sync(0xffffffffu, smem_u32(halo_tiles) + (uint32_t)(hb1 * HALO_BYTES), 0);
+            const uint32_t h_last = nt == 2 ? h1 : h0;
             tc_fence_after();
-            // window shifted by the tap: starts (1+dy) halo rows and (1+dx) pixels in; 8-pixel row groups are one
-            // halo row (16 pixels = 2048 bytes) apart.  The 128-byte swizzle is a function of the shared-memory
-            // address bits, for TMA's writes and the MMA's reads alike, so a start row that is not a multiple of 8
-            // needs nothing else (descriptor base offset 0; measured: a non-zero base offset reads the wrong chunks).
-            const uint32_t r0 = (uint32_t)__shfl_sync(0xffffffffu, my_r0, t);
-            const uint32_t a_addr = halo_addr + r0 * 128u;
-            const uint32_t a_lo = umma_desc_lo(a_addr);
-            const uint32_t a_hi = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
-            const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(p.a_stage_bytes >> 4);
-            if (p.debug & 4) umma_commit_elect(&empty_bar[s]);
-            else umma_f16_kblock_ahi(d, a_lo, a_hi, b_lo, idesc, it ? 1u : 0u, &empty_bar[s]);
-            if (++s == p.stages) {
-              s = 0;
-              ph ^= 1u;
+            for (int t = 0; t < p.ntaps[src]; ++t, ++it) {
+              mbar_wait(&full_bar[s], ph);
+              tc_fence_after();
+              // window shifted by the tap: starts (1+dy) halo rows and (1+dx) pixels in; 8-pixel row groups are one
+              // halo row (10 pixels = 1280 bytes) apart.  The 128-byte swizzle is a function of the shared-memory
+              // address bits, for TMA's writes and the MMA's reads alike, so a start row that is not a multiple of 8
+              // needs nothing else (descriptor base offset 0; measured: a non-zero base offset reads the wrong chunks).
+              const uint32_t r0 = (uint32_t)__shfl_sync(0xffffffffu, src ? my_r1 : my_r0, t);
+              const uint32_t a_hi = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
+              const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(p.a_stage_bytes >> 4);
+              if (p.debug & 4) {
+                umma_commit_elect(&empty_bar[s]);
+              } else {
+                // the same weight tile against every tile of the group; the stage is released after the last one
+                if (nt == 2) umma_f16_kblock_ahi_nc(d0, umma_desc_lo(h0 + r0 * 128u), a_hi, b_lo, idesc, it ? 1u : 0u);
+                umma_f16_kblock_ahi(d_last, umma_desc_lo(h_last + r0 * 128u), a_hi, b_lo, idesc, it ? 1u : 0u, &empty_bar[s]);
+              }
+              if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
+            // the halo tiles are free once their taps have been multiplied
+            umma_commit_elect(&halo_empty[hb0]);
+            if (nt == 2) umma_commit_elect(&halo_empty[hb1]);
           }
-          umma_commit_elect(&halo_empty[hb]);  // the halo tile is free once its nine taps have been multiplied
+        }
+      } else {
+        for (; it < kiters; ++it) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4);
+          if (p.debug & 4) umma_commit_elect(&empty_bar[s]);
+          else umma_f16_kblock(d0, a_lo, a_lo + (uint32_t)(p.a_stage_bytes >> 4), idesc, it ? 1u : 0u, &empty_bar[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
-      for (; it < kiters; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4);
-        if (p.debug & 4) umma_commit_elect(&empty_bar[s]);
-        else umma_f16_kblock(d, a_lo, a_lo + (uint32_t)(p.a_stage_bytes >> 4), idesc, it ? 1u : 0u, &empty_bar[s]);
-        if (++s == p.stages) {
-          s = 0;
-          ph ^= 1u;
-        }
-      }
-      umma_commit_elect(&acc_full[buf]);  // accumulator complete
+      umma_commit_elect(&acc_full[buf0]);  // accumulators complete
+      if (nt == 2) umma_commit_elect(&acc_full[buf1]);
+      lt += nt;
     }
   } else {
     // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 and the 32-column blocks of parity (w-2)/4 =====
@@ -400,7 +445,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     };
     const uint32_t stage0 = smem_u32(stage_smem) + (uint32_t)(warp - 2) * 4096u, stage1 = stage0 + 2048u;
 
-    int tile = blockIdx.x, c0 = half * 32, lt = 0, item = 0;
+    // this CTA's tiles in the order the MMA warp fills the accumulator buffers: group by group, tile by tile
+    auto tile_of = [&](int gi, int gj) {
+      return gi < p.total_groups ? group_cb(gi) * p.tiles_spatial + group_sp0(gi) + gj : p.total_tiles;
+    };
+    auto advance = [&](int& gi, int& gj) {
+      if (gj + 1 < group_nt(gi)) {
+        ++gj;
+      } else {
+        gi += (int)gridDim.x;
+        gj = 0;
+      }
+    };
+    int gi = blockIdx.x, gj = 0;
+    int tile = tile_of(gi, gj), c0 = half * 32, lt = 0, item = 0;
     const bool any = tile < p.total_tiles && c0 < BN;
     float4 pf0, pf1;
     uint4 rv[4];
@@ -420,11 +478,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < 4; ++j) rcur[j] = rv[j];
       const Geom gc = g;
-      const int c0c = c0, buf = lt & 1;
+      const int c0c = c0, buf = lt & bmask;
       const bool first = c0 == half * 32;
-      int ntile = tile, nc0 = c0 + 64;
+      int ntile = tile, nc0 = c0 + 64, ngi = gi, ngj = gj;
       if (nc0 >= BN) {
-        ntile = tile + (int)gridDim.x;
+        advance(ngi, ngj);
+        ntile = tile_of(ngi, ngj);
         nc0 = half * 32;
       }
       const bool last = ntile != tile;
@@ -434,7 +493,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         prefetch_residual(g, nc0, rv);
       }
       if (first) {
-        mbar_wait(&acc_full[buf], ((uint32_t)lt >> 1) & 1u);
+        mbar_wait(&acc_full[buf], ((uint32_t)(lt >> bshift)) & 1u);
         tc_fence_after();
       }
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BNp);
@@ -555,16 +614,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         ++lt;
       }
       tile = ntile;
+      gi = ngi;
+      gj = ngj;
       c0 = nc0;
       ++item;
     }
     // a warp whose column parity has no block in this launch (BN <= 32) still releases every accumulator
     if (!any || half * 32 >= BN) {
       int lt2 = 0;
-      for (int t2 = blockIdx.x; t2 < p.total_tiles; t2 += gridDim.x, ++lt2) {
-        mbar_wait(&acc_full[lt2 & 1], ((uint32_t)lt2 >> 1) & 1u);
-        if (lane == 0) mbar_arrive(&acc_empty[lt2 & 1]);
-      }
+      for (int g2 = blockIdx.x; g2 < p.total_groups; g2 += gridDim.x)
+        for (int j2 = 0; j2 < group_nt(g2); ++j2, ++lt2) {
+          mbar_wait(&acc_full[lt2 & bmask], ((uint32_t)(lt2 >> bshift)) & 1u);
+          if (lane == 0) mbar_arrive(&acc_empty[lt2 & bmask]);
+        }
     }
   }
   tc_fence_before();
@@ -661,6 +723,9 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   for (int t = 0; t < d->in[0].ntaps; ++t)
     halo = halo && d->in[0].dy[t] >= -1 && d->in[0].dy[t] <= 1 && d->in[0].dx[t] >= -1 && d->in[0].dx[t] <= 1;
   halo = halo && d->in[0].ntaps > 1;
+  // the second input (the decoder's fused 1x1 skip) goes through halo tiles too: its taps must lie in the window as well
+  for (int t = 0; t < d->in[1].ntaps; ++t)
+    halo = halo && d->in[1].dy[t] >= -1 && d->in[1].dy[t] <= 1 && d->in[1].dx[t] >= -1 && d->in[1].dx[t] <= 1;
   if (halo) {
     TW = 8;
     TH = 16;
@@ -682,14 +747,30 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   int BN = d->cout_pad <= 256 ? d->cout_pad : 128;
   PS_CHECK_ARG(d->cout_pad % BN == 0);
   p.BN = BN;
-  // a ring stage carries an A tile only if some k-iteration stages one (not input 0 in halo mode)
-  p.a_stage_bytes = (!halo || d->in[1].ntaps > 0) ? A_STAGE_BYTES : 0;
+  // a ring stage carries an A tile only in tap mode (in halo mode every tap of both inputs is read from a halo tile)
+  p.a_stage_bytes = halo ? 0 : A_STAGE_BYTES;
   const int stage_bytes = p.a_stage_bytes + BN * BK * 2;
+  // groups of two tiles share every weight tile: needs four accumulator buffers (4 x BN <= 512 TMEM columns); it
+  // only pays when there are more tiles than SMs (otherwise it would just idle half of them)
+  static thread_local int attr_dev = -1;
+  static thread_local int sms = 148;
+  int dev = 0;
+  PS_CUDA(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    PS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_dev = dev;
+  }
+  p.tiles_spatial = p.tiles_x * p.tiles_y * tiles_n;
+  p.total_tiles = p.tiles_spatial * (d->cout_pad / BN);
+  p.tpg = (halo && BN <= 128 && !(dbg & 1) && p.total_tiles >= 2 * sms) ? 2 : 1;
+  p.nbuf = 2 * p.tpg;
+  p.nhalo = 2 * p.tpg;
   // one persistent CTA per SM: as many ring stages as ~200 KB of shared memory hold
-  int stages = (182 * 1024 - (halo ? 2 * HALO_BYTES : 0)) / stage_bytes;  // 227 KB - barriers, parameter and staging tiles
+  int stages = (182 * 1024 - (halo ? p.nhalo * HALO_BYTES : 0)) / stage_bytes;  // 227 KB - barriers, parameter and staging tiles
   stages = stages > CONV_MAX_STAGES ? CONV_MAX_STAGES : (stages < 2 ? 2 : stages);
   p.stages = stages;
-  CUtensorMap mapA[2], mapW, mapH;
+  CUtensorMap mapA[2], mapW, mapH, mapH1;
   memset(mapA, 0, sizeof(mapA));
   int wrows = 0;
   for (int s = 0; s < 2; ++s) {
@@ -712,11 +793,16 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   if (p.ntaps[1] == 0) mapA[1] = mapA[0];
   int rc = make_w_map(&mapW, d->weights, d->w_rows, d->w_cin_pad, BN);
   if (rc != PS_OK) return rc;
-  mapH = mapA[0];
+  mapH = mapH1 = mapA[0];
   if (halo) {
     const ps_conv_input& in = d->in[0];
     rc = make_act_map(&mapH, in.ptr, d->N, in.H, in.W, in.C, in.cstride, HALO_W, HALO_H, 1, 1);
     if (rc != PS_OK) return rc;
+    if (d->in[1].ntaps > 0) {
+      const ps_conv_input& in1 = d->in[1];
+      rc = make_act_map(&mapH1, in1.ptr, d->N, in1.H, in1.W, in1.C, in1.cstride, HALO_W, HALO_H, 1, 1);
+      if (rc != PS_OK) return rc;
+    }
   }
   p.Cout = d->Cout;
   p.bias = d->bias;
@@ -741,21 +827,13 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.out_py = d->out_py;
   p.out_px = d->out_px;
 
-  const size_t smem_bytes = 1024 + (halo ? 2 * HALO_BYTES : 0) + (size_t)stages * stage_bytes + (2 * stages + 8) * sizeof(uint64_t) + 16 + 8 * 2 * 40 * 16 + 8 * 4096;
-  static thread_local int attr_dev = -1;
-  static thread_local int sms = 148;
-  int dev = 0;
-  PS_CUDA(cudaGetDevice(&dev));
-  if (attr_dev != dev) {
-    PS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_dev = dev;
-  }
-  p.tiles_spatial = p.tiles_x * p.tiles_y * tiles_n;
-  p.total_tiles = p.tiles_spatial * (d->cout_pad / BN);
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const size_t smem_bytes = 1024 + (halo ? p.nhalo * HALO_BYTES : 0) + (size_t)stages * stage_bytes +
+                            (2 * stages + 16) * sizeof(uint64_t) + 16 + 8 * 2 * 40 * 16 + 8 * 4096;
+  p.groups_per_cb = (p.tiles_spatial + p.tpg - 1) / p.tpg;
+  p.total_groups = p.groups_per_cb * (d->cout_pad / BN);
+  const int grid = p.total_groups < sms ? p.total_groups : sms;
   PS_TIME_BEGIN("conv_igemm_kernel", (cudaStream_t)stream);
-  conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, (cudaStream_t)stream>>>(mapA[0], mapA[1], mapW, mapH, p);
+  conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, (cudaStream_t)stream>>>(mapA[0], mapA[1], mapW, mapH, mapH1, p);
   PS_TIME_END((cudaStream_t)stream);
   PS_LAUNCHED();
   return PS_OK;

@@ -269,6 +269,32 @@ __device__ __forceinline__ void umma_f16_kblock_ahi(uint32_t tmem_d, uint32_t a_
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128), "r"(smem_u32(commit_bar)), "r"(a_hi)
       : "memory");
 }
+// the same without the trailing commit (another tile's MMAs against the same weight stage follow)
+__device__ __forceinline__ void umma_f16_kblock_ahi_nc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                       uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.s64 da, da, 2;\n\t"
+      "add.s64 db, db, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(UMMA_DESC_HI_SW128), "r"(a_hi)
+      : "memory");
+}
 // The same K block with the A operand in tensor memory (A-from-TMEM form): the row's 64 K values are 32 consecutive
 // 32-bit columns of its lane (two fp16 per column, even k in the low half), 8 columns per K=16 step.
 __device__ __forceinline__ void umma_f16_ts_kblock(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,

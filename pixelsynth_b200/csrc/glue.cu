@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostpool.cuh"
 
 namespace ps {
 
@@ -138,9 +139,14 @@ extern "C" int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, in
       const uint8_t* m = bg_mask_host + (size_t)b * S * S;
       for (int r = 0; r < G; ++r)
         for (int c = 0; c < G; ++c) {
+          // 64 mask bytes (0 / 1) of the cell: eight 8-byte words, byte sums by multiplication
           int cnt = 0;
-          for (int y = 0; y < 8; ++y)
-            for (int x = 0; x < 8; ++x) cnt += m[(size_t)(r * 8 + y) * S + c * 8 + x] ? 1 : 0;
+          for (int y = 0; y < 8; ++y) {
+            uint64_t v;
+            memcpy(&v, m + (size_t)(r * 8 + y) * S + c * 8, 8);
+            v = (v | (v >> 1) | (v >> 2) | (v >> 3) | (v >> 4) | (v >> 5) | (v >> 6) | (v >> 7)) & 0x0101010101010101ull;  // any non-zero byte counts once
+            cnt += (int)((v * 0x0101010101010101ull) >> 56);
+          }
           bg[r * G + c] = cnt == 64;  // AvgPool2d(8) -> astype(uint8): 1 only when every pixel agrees
           fg[r * G + c] = cnt == 0;
           sample_mask_host[(size_t)b * G * G + r * G + c] = cnt == 64;  // sample.py:29 `== 1`
@@ -167,16 +173,7 @@ extern "C" int ps_lmconv_glue_host(const uint8_t* bg_mask_host, int B, int S, in
   if (nth <= 1) {
     work(0, B);
   } else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < nth; ++t) {
-      const int lo = (int)((long long)B * t / nth), hi = (int)((long long)B * (t + 1) / nth);
-      try {
-        th.emplace_back(work, lo, hi);
-      } catch (...) {  // thread creation failed: std::system_error must not cross the C ABI, do the share inline
-        work(lo, hi);
-      }
-    }
-    for (auto& x : th) x.join();
+    HostPool::get().run(nth, [&](int t) { work((int)((long long)B * t / nth), (int)((long long)B * (t + 1) / nth)); });
   }
   return PS_OK;
 }

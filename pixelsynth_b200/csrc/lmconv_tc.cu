@@ -46,6 +46,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostpool.cuh"
 #include "tc05.cuh"
 
 namespace ps {
@@ -1317,22 +1318,8 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
   if (const char* e = getenv("PS_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));  // tests pin the worker count
   const int T = std::max(1, std::min({(int)(hw ? hw : 1), 32, B / 4}));
   std::vector<int> tops_a(T, -1), tops_b(T, -1), bad(T, 0);
-  // worker c runs fn(c); a thread that cannot be created (std::system_error must not cross the C ABI) is run inline
-  auto run_workers = [&](auto&& fn) {
-    if (T == 1) {
-      fn(0);
-      return;
-    }
-    std::vector<std::thread> th;
-    for (int c = 0; c < T; ++c) {
-      try {
-        th.emplace_back(fn, c);
-      } catch (...) {
-        fn(c);
-      }
-    }
-    for (auto& t : th) t.join();
-  };
+  // worker c runs fn(c) on the library's persistent host team (hostpool.cuh)
+  auto run_workers = [&](auto&& fn) { HostPool::get().run(T, fn); };
   auto image_range = [&](int c, int& lo, int& hi) {
     lo = (int)((long long)B * c / T);
     hi = (int)((long long)B * (c + 1) / T);

@@ -19,9 +19,7 @@ from oracle import nets_ref, weights  # noqa: E402
 import os as _os
 import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
-from _ref_import import use_reference_models  # noqa: E402
-
-use_reference_models()
+from _ref_import import use_reference_models  # noqa: E402  (called from __main__ only: importing this file must not rebind `models`)
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -130,4 +128,5 @@ def main():
 
 
 if __name__ == "__main__":
+    use_reference_models()
     main()

@@ -26,9 +26,7 @@ from oracle import splat_ref  # noqa: E402
 import os as _os
 import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
-from _ref_import import use_reference_models  # noqa: E402
-
-use_reference_models()
+from _ref_import import use_reference_models  # noqa: E402  (called from __main__ only: importing this file must not rebind `models`)
 
 REF = "/root/reference"
 CAPTURE = {}
@@ -196,6 +194,7 @@ def run_cumulative(name, W=32, K=16, radius_px=3.0, n_views=3, seed=5):
 
 
 if __name__ == "__main__":
+    use_reference_models()
     install_stubs()
     if "--cumulative-only" in sys.argv:
         run_cumulative("cumul_w32_k16")

@@ -15,9 +15,7 @@ sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
 import os as _os
 import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
-from _ref_import import use_reference_models  # noqa: E402
-
-use_reference_models()
+from _ref_import import use_reference_models  # noqa: E402  (called from __main__ only: importing this file must not rebind `models`)
 
 class Opt(dict):
     __getattr__ = dict.get
@@ -53,4 +51,5 @@ def main():
 
 
 if __name__ == "__main__":
+    use_reference_models()
     main()

@@ -59,6 +59,10 @@ struct ConvKernelParams {
   int tpg, groups_per_cb, total_groups;
   int nbuf;         // TMEM accumulator buffers (2 * tpg): the epilogue of one group overlaps the main loop of the next
   int nhalo;        // halo buffers (2 * tpg)
+  // Narrow layers (Cout <= 16, e.g. the 128 -> 3 and 3 -> 3 convolutions at 256 x 256): a tap's weight tile is 2 KB and
+  // a tile's main loop is 18 of them, each a TMA round trip -- the layer was bound by TMA latency, not by any roofline.
+  // wgroup = taps of input 0 whose weight tiles one TMA brings into one ring stage (ntaps[0] there, 1 elsewhere).
+  int wgroup;
   int debug;
   // epilogue
   int Cout;  // real output channels (columns >= Cout are dropped)
@@ -137,13 +141,14 @@ __device__ __forceinline__ void stage_block32(const float* f, const float4* sc, 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH,
-                      const __grid_constant__ CUtensorMap mapH1, const ConvKernelParams p) {
+                      const __grid_constant__ CUtensorMap mapH1, const __grid_constant__ CUtensorMap mapWG,
+                      const ConvKernelParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform to the compiler as well
   const int BN = p.BN;
   const int BNp = (BN + 31) & ~31;  // TMEM columns per accumulator buffer
-  const int stage_bytes = p.a_stage_bytes + BN * BK * 2;
+  const int stage_bytes = p.a_stage_bytes + p.wgroup * BN * BK * 2;
   // carve: [nhalo halo tiles (halo mode)] [stages x (A | B)] then barriers
   unsigned char* halo_tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = halo_tiles + (p.halo ? p.nhalo * HALO_BYTES : 0);
@@ -229,15 +234,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
               }
               __syncwarp();
             }
-            for (int t = 0; t < p.ntaps[src]; ++t) {
+            const int wg = src ? 1 : p.wgroup;  // taps per weight stage
+            for (int t = 0; t < p.ntaps[src]; t += wg) {
               const int wr = __shfl_sync(0xffffffffu, src ? my_w1 : my_w0, t);
               mbar_wait(&empty_bar[s], ph);
               if (elect_one()) {
                 if (p.debug & 8) {
                   mbar_arrive(&full_bar[s]);
                 } else {
-                  mbar_expect_tx(&full_bar[s], w_bytes);
-                  tma_load_2d(&mapW, &full_bar[s], tiles + (size_t)s * stage_bytes + p.a_stage_bytes, kc * BK, wr + ncol0);
+                  mbar_expect_tx(&full_bar[s], w_bytes * (uint32_t)wg);
+                  tma_load_2d(wg > 1 ? &mapWG : &mapW, &full_bar[s], tiles + (size_t)s * stage_bytes + p.a_stage_bytes, kc * BK,
+                              wr + ncol0);
                 }
               }
               __syncwarp();
@@ -312,24 +319,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             const uint32_t h1 = __shfl_sync(0xffffffffu, smem_u32(halo_tiles) + (uint32_t)(hb1 * HALO_BYTES), 0);
             const uint32_t h_last = nt == 2 ? h1 : h0;
             tc_fence_after();
+            const int wg = src ? 1 : p.wgroup;
             for (int t = 0; t < p.ntaps[src]; ++t, ++it) {
-              mbar_wait(&full_bar[s], ph);
-              tc_fence_after();
+              const bool opens = wg == 1 || t == 0, releases = wg == 1 || t == p.ntaps[src] - 1;
+              if (opens) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+              }
               // window shifted by the tap: starts (1+dy) halo rows and (1+dx) pixels in; 8-pixel row groups are one
               // halo row (10 pixels = 1280 bytes) apart.  The 128-byte swizzle is a function of the shared-memory
               // address bits, for TMA's writes and the MMA's reads alike, so a start row that is not a multiple of 8
               // needs nothing else (descriptor base offset 0; measured: a non-zero base offset reads the wrong chunks).
               const uint32_t r0 = (uint32_t)__shfl_sync(0xffffffffu, src ? my_r1 : my_r0, t);
               const uint32_t a_hi = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
-              const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(p.a_stage_bytes >> 4);
+              const uint32_t b_lo = a_lo0 + (uint32_t)s * (uint32_t)(stage_bytes >> 4) + (uint32_t)(p.a_stage_bytes >> 4) +
+                                    (wg > 1 ? (uint32_t)(t * BN * 8) : 0u);  // tap t's tile inside a grouped stage
               if (p.debug & 4) {
-                umma_commit_elect(&empty_bar[s]);
+                if (releases) umma_commit_elect(&empty_bar[s]);
               } else {
-                // the same weight tile against every tile of the group; the stage is released after the last one
+                // the same weight tile against every tile of the group; the stage is released after its last use
                 if (nt == 2) umma_f16_kblock_ahi_nc(d0, umma_desc_lo(h0 + r0 * 128u), a_hi, b_lo, idesc, it ? 1u : 0u);
-                umma_f16_kblock_ahi(d_last, umma_desc_lo(h_last + r0 * 128u), a_hi, b_lo, idesc, it ? 1u : 0u, &empty_bar[s]);
+                if (releases) umma_f16_kblock_ahi(d_last, umma_desc_lo(h_last + r0 * 128u), a_hi, b_lo, idesc, it ? 1u : 0u, &empty_bar[s]);
+                else umma_f16_kblock_ahi_nc(d_last, umma_desc_lo(h_last + r0 * 128u), a_hi, b_lo, idesc, it ? 1u : 0u);
               }
-              if (++s == p.stages) {
+              if (releases && ++s == p.stages) {
                 s = 0;
                 ph ^= 1u;
               }
@@ -749,7 +762,14 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.BN = BN;
   // a ring stage carries an A tile only in tap mode (in halo mode every tap of both inputs is read from a halo tile)
   p.a_stage_bytes = halo ? 0 : A_STAGE_BYTES;
-  const int stage_bytes = p.a_stage_bytes + BN * BK * 2;
+  // narrow layers: all taps' weight tiles of a 64-channel chunk in one TMA / one stage (rows must be tap-contiguous)
+  p.wgroup = 1;
+  if (halo && BN == d->cout_pad && d->in[0].ntaps * BN <= 256 && !(dbg & 256)) {
+    bool contiguous = true;
+    for (int t = 0; t < d->in[0].ntaps; ++t) contiguous = contiguous && d->in[0].wrow[t] == d->in[0].wrow[0] + t * BN;
+    if (contiguous) p.wgroup = d->in[0].ntaps;
+  }
+  const int stage_bytes = p.a_stage_bytes + p.wgroup * BN * BK * 2;
   // groups of two tiles share every weight tile: needs four accumulator buffers (4 x BN <= 512 TMEM columns); it
   // only pays when there are more tiles than SMs (otherwise it would just idle half of them)
   static thread_local int attr_dev = -1;
@@ -770,7 +790,7 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   int stages = (182 * 1024 - (halo ? p.nhalo * HALO_BYTES : 0)) / stage_bytes;  // 227 KB - barriers, parameter and staging tiles
   stages = stages > CONV_MAX_STAGES ? CONV_MAX_STAGES : (stages < 2 ? 2 : stages);
   p.stages = stages;
-  CUtensorMap mapA[2], mapW, mapH, mapH1;
+  CUtensorMap mapA[2], mapW, mapH, mapH1, mapWG;
   memset(mapA, 0, sizeof(mapA));
   int wrows = 0;
   for (int s = 0; s < 2; ++s) {
@@ -793,6 +813,11 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   if (p.ntaps[1] == 0) mapA[1] = mapA[0];
   int rc = make_w_map(&mapW, d->weights, d->w_rows, d->w_cin_pad, BN);
   if (rc != PS_OK) return rc;
+  mapWG = mapW;
+  if (p.wgroup > 1) {
+    rc = make_w_map(&mapWG, d->weights, d->w_rows, d->w_cin_pad, p.wgroup * BN);
+    if (rc != PS_OK) return rc;
+  }
   mapH = mapH1 = mapA[0];
   if (halo) {
     const ps_conv_input& in = d->in[0];
@@ -833,7 +858,7 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.total_groups = p.groups_per_cb * (d->cout_pad / BN);
   const int grid = p.total_groups < sms ? p.total_groups : sms;
   PS_TIME_BEGIN("conv_igemm_kernel", (cudaStream_t)stream);
-  conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, (cudaStream_t)stream>>>(mapA[0], mapA[1], mapW, mapH, mapH1, p);
+  conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, (cudaStream_t)stream>>>(mapA[0], mapA[1], mapW, mapH, mapH1, mapWG, p);
   PS_TIME_END((cudaStream_t)stream);
   PS_LAUNCHED();
   return PS_OK;

@@ -470,7 +470,7 @@ def main():
         step_resident()
     torch.cuda.synchronize()
     L.ps_timing_enable(0)
-    kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "conv_igemm_kernel", "lmconv_tc_kernel")}
+    kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "fine_big_kernel", "conv_igemm_kernel", "lmconv_tc_kernel")}
     _lib.kernel_time_ms(None)
     last = model.last
     # the splat in its map-emitting mode (idx + z maps: the bit-exact parity surface, 69.0 MB/view): the HBM-bound
@@ -555,6 +555,7 @@ def main():
     rl = {
         "splat fine_kernel": {"bound": "hbm", "achieved": BYTES_PER_VIEW_SPLAT_FUSED * B / (per_step["fine_kernel"][0] * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s", "ms_per_step": per_step["fine_kernel"][0],
+                              "overflow_tiles_ms_per_step": per_step["fine_big_kernel"][0],
                               "note": "maps suppressed inside the pipeline (1.90 MB/view: compute bound); the map-emitting "
                                       "mode (69.0 MB/view) is the line below, measured in the same run; DESIGN.md section 4"},
         "lmconv_tc_kernel": {"bound": "tensor", "achieved": FLOP_PER_CELL * cells_processed / (per_step["lmconv_tc_kernel"][0] * 1e-3) / 1e12,

@@ -21,6 +21,7 @@
 // Bit-exact surfaces (idx, zbuf, dist2, pts) use __f*_rn intrinsics so ptxas never contracts to FMA;
 // this matches oracle/splat_oracle.c built with -ffp-contract=off.
 #include "common.cuh"
+#include "tc05.cuh"
 
 namespace ps {
 
@@ -354,6 +355,7 @@ struct FineSmem {
   float ndcx[TILE], ndcy[TILE];  // NDC centres of the tile's pixel columns / rows
   unsigned zmin, zmax, maxcount;
   unsigned warp_tot[FTPB / 32];
+  unsigned long long list_bar;  // mbarrier of the bulk copy that stages the tile's candidate list (into bw, free until the scatter)
 };
 
 __device__ __forceinline__ float4 gather_feat(const float* __restrict__ featb, int C, int P, int pid) {
@@ -474,6 +476,20 @@ __global__ void __launch_bounds__(FTPB, 6) fine_kernel(FineParams q) {
   const int S = q.S, K = q.K, P = q.P, C = q.C;
 
   // ---- A. load + sort ----
+  // The tile's candidate list (a contiguous run of point ids, at most 2 KB) is staged with ONE bulk asynchronous copy
+  // (cp.async.bulk, the descriptor-less TMA path), issued first so that it flies while the CTA clears its histogram and
+  // builds its NDC tables; the point records themselves are gathers by id, which no bulk copy expresses.
+  int* ids_s = reinterpret_cast<int*>(sm.bw);
+  uint64_t* lbar = reinterpret_cast<uint64_t*>(&sm.list_bar);
+  if (tid == 0) {
+    mbar_init(lbar, 1);
+    mbar_fence_init();
+    if (n > 0) {
+      const uint32_t bytes = (uint32_t)(n * 4 + 15) & ~15u;
+      mbar_expect_tx(lbar, bytes);
+      bulk_load(ids_s, q.list + ((size_t)b * nt2 + t) * CAPG, bytes, lbar);
+    }
+  }
   for (int i = tid; i < (NB + 4) / 4; i += FTPB) reinterpret_cast<uint4*>(sm.u.s.hist)[i] = make_uint4(0, 0, 0, 0);
   if (tid < TILE) sm.ndcx[tid] = pix_to_ndc(S - 1 - (tx * TILE + tid), S);
   if (tid >= 32 && tid < 32 + TILE) sm.ndcy[tid - 32] = pix_to_ndc(S - 1 - (ty * TILE + tid - 32), S);
@@ -484,15 +500,16 @@ __global__ void __launch_bounds__(FTPB, 6) fine_kernel(FineParams q) {
     sm.maxcount = 0u;
   }
   const int32_t idbase = (int32_t)((size_t)b * P);  // stored candidate ids are packed: b*P + p
-  const int* lst = q.list + ((size_t)b * nt2 + t) * CAPG;
   const float4* p4 = q.pts4 + (size_t)b * P;
+  __syncthreads();  // the list barrier is initialised (and armed) before anybody waits on it
+  if (n > 0) mbar_wait(lbar, 0);
   int id[PER];
   float cx[PER], cy[PER], cz[PER];
   unsigned zb[PER];
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const int i = tid + j * FTPB;
-    id[j] = (i < n) ? __ldg(lst + i) : 0;
+    id[j] = (i < n) ? ids_s[i] : 0;
   }
   unsigned lmin = 0xffffffffu, lmax = 0u;
 #pragma unroll
@@ -805,18 +822,21 @@ __global__ void __launch_bounds__(FTPB, 6) fine_kernel(FineParams q) {
 // Overflow path: tiles with more than CAP candidates.  Streams the candidates in chunks of CAPB (from the
 // tile's list, or by rescanning the whole cloud when even the list overflowed), sorts each chunk, and merges
 // the chunk's hits (already ordered) into each pixel's running top-K.  Slow, exact, never drops a point.
+constexpr int BTH = 256;  // threads of the overflow kernel: all sort / fill / write, the first NPIX each own a pixel's top-K
 struct BigSmem {
   unsigned long long key[CAPB];
   float2 xy[CAPB];
   unsigned long long topA[MAXK][TPB];
   unsigned long long topB[MAXK][TPB];
-  int id4[TPB / 32][MAXK];
-  float z4[TPB / 32][MAXK];
-  float d4[TPB / 32][MAXK];
-  float w4[TPB / 32][MAXK];
+  int id4[BTH / 32][MAXK];
+  float z4[BTH / 32][MAXK];
+  float d4[BTH / 32][MAXK];
+  float w4[BTH / 32][MAXK];
+  int cnt[TPB];   // hits kept per pixel
+  int fill;
 };
 
-__global__ void __launch_bounds__(TPB) fine_big_kernel(FineParams q) {
+__global__ void __launch_bounds__(BTH) fine_big_kernel(FineParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BigSmem& sm = *reinterpret_cast<BigSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -830,72 +850,98 @@ __global__ void __launch_bounds__(TPB) fine_big_kernel(FineParams q) {
     const int n = q.tile_count[bt];
     const bool rescan = n > CAPG;  // the list is incomplete: derive the candidates from the whole cloud
     const int total = rescan ? P : n;
-    const int xi = tx * TILE + (tid & 7), yi = ty * TILE + (tid >> 3);
-    const bool inimg = xi < S && yi < S;
+    const bool owner = tid < TPB;  // this thread merges pixel `tid` of the tile
+    const int xi = tx * TILE + (tid & 7), yi = ty * TILE + ((tid >> 3) & 7);
     const float xf = pix_to_ndc(S - 1 - xi, S), yf = pix_to_ndc(S - 1 - yi, S);
     const float4* p4 = q.pts4 + (size_t)b * P;
     const int* lst = q.list + (size_t)bt * CAPG;
     unsigned long long(*A)[TPB] = sm.topA;
     unsigned long long(*Bv)[TPB] = sm.topB;
     int cntA = 0;
-    for (int c0 = 0; c0 < total; c0 += CAPB) {
-      const int m = min(CAPB, total - c0);
+    for (int c0 = 0; c0 < total;) {
+      // fill the chunk: the next CAPB list entries, or (rescan) the next points of the cloud whose tile range covers
+      // this tile, compacted -- the order inside a chunk is irrelevant (it is sorted below), and so is the chunking
+      // (the merge keeps the K smallest keys)
+      int m;
+      __syncthreads();
+      if (!rescan) {
+        m = min(CAPB, total - c0);
+        for (int i = tid; i < m; i += BTH) {
+          const int p = lst[c0 + i];
+          sm.key[i] = ((unsigned long long)__float_as_uint(p4[p].z + 0.0f) << 32) | (unsigned)p;
+        }
+        c0 += m;
+      } else {
+        if (tid == 0) sm.fill = 0;
+        __syncthreads();
+        m = 0;
+        while (c0 < total && m <= CAPB - 2 * BTH) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int p = c0 + e * BTH + tid;
+            bool take = false;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < total) {
+              v = p4[p];
+              int a0, a1, b0, b1;
+              take = tile_range(v.x, v.y, v.z, q.g, a0, a1, b0, b1) && tx >= a0 && tx <= a1 && ty >= b0 && ty <= b1;
+            }
+            const unsigned bal = __ballot_sync(FULL, take);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&sm.fill, __popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (take)
+              sm.key[base + __popc(bal & ((1u << lane) - 1))] =
+                  ((unsigned long long)__float_as_uint(v.z + 0.0f) << 32) | (unsigned)p;
+          }
+          c0 += 2 * BTH;
+          __syncthreads();
+          m = sm.fill;
+        }
+        if (m == 0) continue;  // (only at the end of the cloud)
+      }
       int N = 2;
       while (N < m) N <<= 1;
+      for (int i = m + tid; i < N; i += BTH) sm.key[i] = ~0ull;
       __syncthreads();
-      for (int i = tid; i < N; i += TPB) {
-        unsigned long long key = ~0ull;
-        if (i < m) {
-          const int p = rescan ? (c0 + i) : lst[c0 + i];
-          const float4 v = p4[p];
-          bool take = true;
-          if (rescan) {
-            int a0, a1, b0, b1;
-            take = tile_range(v.x, v.y, v.z, q.g, a0, a1, b0, b1) && tx >= a0 && tx <= a1 && ty >= b0 && ty <= b1;
+      bitonic_sort_u64(sm.key, N, tid, BTH);
+      for (int i = tid; i < m; i += BTH) {
+        const float4 v = p4[(int)(unsigned)(sm.key[i] & 0xffffffffull)];
+        sm.xy[i] = make_float2(-v.x, -v.y);
+      }
+      __syncthreads();
+      if (owner) {
+        // merge: A (sorted, cntA) with this chunk's hits (sorted) -> Bv, keeping the K smallest
+        int ia = 0, nb = 0;
+        for (int i = 0; i < m; ++i) {
+          const float2 c = sm.xy[i];
+          const float d2 = dist2_rn(__fsub_rn(c.x, xf), __fsub_rn(c.y, yf));
+          if (d2 < q.r2 && nb < K) {
+            const unsigned long long key = sm.key[i];
+            while (ia < cntA && nb < K && A[ia][tid] < key) Bv[nb++][tid] = A[ia++][tid];
+            if (nb < K) Bv[nb++][tid] = key;
           }
-          if (take) key = ((unsigned long long)__float_as_uint(v.z + 0.0f) << 32) | (unsigned)p;
         }
-        sm.key[i] = key;
+        while (ia < cntA && nb < K) Bv[nb++][tid] = A[ia++][tid];
+        cntA = nb;
       }
-      __syncthreads();
-      bitonic_sort_u64(sm.key, N, tid, TPB);
-      for (int i = tid; i < m; i += TPB) {
-        const unsigned long long key = sm.key[i];
-        if (key != ~0ull) {
-          const float4 v = p4[(int)(unsigned)(key & 0xffffffffull)];
-          sm.xy[i] = make_float2(-v.x, -v.y);
-        }
-      }
-      __syncthreads();
-      // merge: A (sorted, cntA) with this chunk's hits (sorted) -> Bv, keeping the K smallest
-      int ia = 0, nb = 0;
-      for (int i = 0; i < m; ++i) {
-        const unsigned long long key = sm.key[i];
-        if (key == ~0ull) break;  // rejected entries sort to the end
-        const float2 c = sm.xy[i];
-        const float d2 = dist2_rn(__fsub_rn(c.x, xf), __fsub_rn(c.y, yf));
-        if (d2 < q.r2 && nb < K) {
-          while (ia < cntA && nb < K && A[ia][tid] < key) Bv[nb++][tid] = A[ia++][tid];
-          if (nb < K) Bv[nb++][tid] = key;
-        }
-      }
-      while (ia < cntA && nb < K) Bv[nb++][tid] = A[ia++][tid];
-      cntA = nb;
       unsigned long long(*tmp)[TPB] = A;
       A = Bv;
       Bv = tmp;
     }
-    if (inimg) q.empty[((size_t)b * S + yi) * S + xi] = (cntA == 0);
-    __syncwarp();
-    // one lane per output slot; coordinates and features are gathered from global memory
+    if (owner) {
+      sm.cnt[tid] = cntA;
+      if (xi < S && yi < S) q.empty[((size_t)b * S + yi) * S + xi] = (cntA == 0);
+    }
+    __syncthreads();
+    // every warp writes NPIX / 8 pixels: one lane per output slot; coordinates and features from global memory
     const int rounds = (K + 31) >> 5;
     const int32_t base = (int32_t)((size_t)b * P);
-    for (int j = 0; j < 32; ++j) {
-      if (!__shfl_sync(FULL, (int)inimg, j)) continue;
-      const int pix = warp * 32 + j;
-      const int nh = __shfl_sync(FULL, cntA, j);
-      const float xfj = __shfl_sync(FULL, xf, j), yfj = __shfl_sync(FULL, yf, j);
+    for (int pix = warp; pix < TPB; pix += BTH / 32) {
       const int pxi = tx * TILE + (pix & 7), pyi = ty * TILE + (pix >> 3);
+      if (pxi >= S || pyi >= S) continue;
+      const int nh = sm.cnt[pix];
+      const float xfj = pix_to_ndc(S - 1 - pxi, S), yfj = pix_to_ndc(S - 1 - pyi, S);
       float tcarry = 1.0f, wsum = 0.0f;
       for (int r = 0; r < rounds; ++r) {
         const int k = r * 32 + lane;
@@ -948,12 +994,15 @@ __global__ void __launch_bounds__(TPB) fine_big_kernel(FineParams q) {
       }
       const float norm = fmaxf(wsum, 1e-4f);
       const int nhk = min(nh, K);
-      for (int c = lane; c < C; c += 32) {
+      // lanes share the K slots of one channel (independent loads in flight), then the warp adds the partial sums
+      for (int c = 0; c < C; ++c) {
         const float* fc = q.feat + ((size_t)b * C + c) * P - base;
         float v = 0.0f;
-        for (int k = 0; k < nhk; ++k) v += sm.w4[warp][k] * fc[sm.id4[warp][k]];
+        for (int k = lane; k < nhk; k += 32) v += sm.w4[warp][k] * fc[sm.id4[warp][k]];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
         if (q.accumulation == PS_ACCUM_WSUMNORM) v = v / norm;
-        q.out[(((size_t)b * C + c) * S + pyi) * S + pxi] = v;
+        if (lane == 0) q.out[(((size_t)b * C + c) * S + pyi) * S + pxi] = v;
       }
       __syncwarp();
     }
@@ -1117,7 +1166,9 @@ static int splat_impl(const float* depth, const float* mats, int W, float eps, c
       fine_kernel<false, 4><<<grid, FTPB, sizeof(FineSmem), stream>>>(q);
     PS_TIME_END(stream);
     PS_LAUNCHED();
-    fine_big_kernel<<<296, TPB, sizeof(BigSmem), stream>>>(q);
+    PS_TIME_BEGIN("fine_big_kernel", stream);
+    fine_big_kernel<<<148, BTH, sizeof(BigSmem), stream>>>(q);
+    PS_TIME_END(stream);
     PS_LAUNCHED();
   }
   {

@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--num_split", type=int, default=2, help="scene sweep splits per direction (scripts/demo_scene.sh: 32)")
     ap.add_argument("--cpu-tokens", type=int, default=16, help="sampler tokens timed per step for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="batches in flight per GPU (pixelsynth_b200.pipeline.ViewPipeline); 1 = one forward at a time")
+    ap.add_argument("--sampler-sms", type=int, default=24, help="SMs of the sampler's green-context partition (in-flight > 1)")
     return ap.parse_args()
 
 
@@ -92,6 +95,11 @@ def workload_config(args, world):
         "l2_policy": "activations + sampler cache per step (> 1 GB at batch 32) exceed the 126 MB L2; no explicit flush",
         "parallelism": "images sharded across ranks; one NCCL broadcast of the source images at job start" if world > 1
                        else "single GPU",
+        "in_flight": max(1, args.in_flight),
+        "schedule": ("%d steps in flight per GPU (pixelsynth_b200.pipeline.ViewPipeline): step k+1's sampler launch runs on a "
+                     "%d-SM green-context partition beside step k's refinement decoder on the other SMs; all K steps complete "
+                     "inside the timed region" % (args.in_flight, args.sampler_sms)) if args.in_flight > 1
+                    else "one step at a time on the whole device",
     }
 
 
@@ -406,7 +414,23 @@ def main():
     noise = torch.randn(16, B, 20, generator=g).to(dev)
     uniforms = torch.rand(B, 1024, generator=g)
 
+    # `--in-flight` batches per GPU: batch k+1's sampler (a latency-bound chain on a few SMs) runs on its own SM partition
+    # beside batch k's refinement decoder (pixelsynth_b200/pipeline.py).  Every step's work is inside the timed region:
+    # the loop is drained before the closing event.
+    from pixelsynth_b200.pipeline import ViewPipeline
+    pipe = ViewPipeline(model, depth=max(1, args.in_flight), sampler_sms=args.sampler_sms)
+    pending = []
+
     def step_resident():
+        pending.append(pipe.submit(dev_batch, noise=noise, uniforms=uniforms))
+        if len(pending) >= pipe.depth:
+            pipe.result(pending.pop(0), host_wait=False)
+
+    def drain():
+        while pending:
+            pipe.result(pending.pop(0), host_wait=False)
+
+    def step_serial():
         return model.forward(dev_batch, noise=noise, uniforms=uniforms)[1]["PredImg"]
 
     def barrier():
@@ -414,15 +438,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, drain=lambda: None):
         for _ in range(warmup):
             fn()
+        drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         L.ps_launch_count_reset()
         e0.record()
         for _ in range(steps):
             fn()
+        drain()                                # the current stream now waits for every batch in flight
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -440,39 +466,53 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res, launches, ms_res_ranks = timed(step_resident, args.steps, args.warmup)
+    ms_res, launches, ms_res_ranks = timed(step_resident, args.steps, args.warmup, drain)
     clocks = sampler.stop() if rank == 0 else None
+    ms_serial, _, _ = timed(step_serial, args.steps, 1) if pipe.depth > 1 else (ms_res, 0, 0)   # one forward at a time: the step's latency
 
     # ---- e2e through the reference-facing wrapper with host buffers ----
     bm = BaseModel(model, opt)
     pin = lambda t: t.pin_memory()
     pinned = {"images": [pin(t) for t in host_batch["images"]],
               "cameras": [{k: pin(v) for k, v in c.items()} for c in host_batch["cameras"]]}
-    h_out = torch.empty((B, 3, W, W)).pin_memory()
+    h_outs = [torch.empty((B, 3, W, W)).pin_memory() for _ in range(pipe.depth)]
+    h_out = h_outs[0]
     model_kw = dict(noise=noise, uniforms=uniforms)
+    e2e_n = [0]
 
     def step_e2e():
-        _, out = model.forward(pinned, **model_kw)       # process_batch copies H2D (non_blocking from pinned memory)
-        img = 0.5 * out["PredImg"] + 0.5                  # BaseModel's rescale (base_model.py:96-99)
-        h_out.copy_(img, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # every step: H2D of its images + cameras from pinned memory (process_batch, on the batch's stream), forward,
+        # BaseModel's rescale (base_model.py:96-99), D2H of the result into pinned memory; the host then waits for the
+        # OLDEST batch in flight and owns its pixels
+        dst = h_outs[e2e_n[0] % pipe.depth]
+        e2e_n[0] += 1
+        pending.append(pipe.submit(pinned, then=lambda loss, out: dst.copy_(0.5 * out["PredImg"] + 0.5, non_blocking=True),
+                                   **model_kw))
+        if len(pending) >= pipe.depth:
+            pipe.result(pending.pop(0), host_wait=True)
 
-    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+    def drain_host():
+        while pending:
+            pipe.result(pending.pop(0), host_wait=True)
+
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup), drain_host)
     h2d = sum(t.numel() * 4 for t in pinned["images"]) + sum(v.numel() * 4 for c in pinned["cameras"] for v in c.values())
     d2h = h_out.numel() * 4
 
     # ---- per-kernel device time over the same step (CUDA events recorded by the library on the launching stream) ----
     step_resident()
+    drain()
     torch.cuda.synchronize()
     _lib.kernel_time_ms(None)
     L.ps_timing_enable(1)
     for _ in range(args.steps):
         step_resident()
+    drain()
     torch.cuda.synchronize()
     L.ps_timing_enable(0)
     kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "fine_big_kernel", "conv_igemm_kernel", "lmconv_tc_kernel")}
     _lib.kernel_time_ms(None)
-    last = model.last
+    last = pipe.last(0)
     # the splat in its map-emitting mode (idx + z maps: the bit-exact parity surface, 69.0 MB/view): the HBM-bound
     # configuration SURVEY 8d defines the splat roofline on.  Same depth / cameras as the step, 16 views per launch.
     from pixelsynth_b200.ops import pack_mats as pack_mats_t
@@ -589,10 +629,20 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
+    n_small, n_big = pipe.sm_counts if pipe.sm_counts else (0, 0)
     for k, v in rl.items():
         v["frac"] = v["achieved"] / v["peak"]
         v["share_of_step"] = 0.0 if ("maps" in k or "config 3" in k) else v["ms_per_step"] / step_ms
-    dom = max((k for k in rl if "maps" not in k and "config 3" not in k), key=lambda k: rl[k]["ms_per_step"])
+        if n_big and k in ("conv_igemm_kernel", "lmconv_tc_kernel"):
+            # inside the timed step the kernel is confined to its partition and runs beside the other one: `frac` stays
+            # against the WHOLE device's measured peak (a kernel on 124 of 148 SMs cannot exceed 0.84); shares of
+            # concurrent kernels add up to more than 1
+            v["sms"] = n_big if k == "conv_igemm_kernel" else n_small
+            v["frac_of_partition_peak"] = v["frac"] * (n_small + n_big) / v["sms"]
+    # dominant = the kernel holding the largest share of the device (duration x the SMs it may occupy): with two steps in
+    # flight the sampler's launch is long but confined to its small partition
+    dom = max((k for k in rl if "maps" not in k and "config 3" not in k),
+              key=lambda k: rl[k]["ms_per_step"] * rl[k].get("sms", n_small + n_big or 1))
     roof = dict(rl[dom])
     roof.update({"kernel": dom, "traffic": traffic.get(dom), "traffic_source": traffic.get("source"), "peak_source": peak_src})
     views_per_step = B * world
@@ -601,12 +651,17 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": views_per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "api": "ZbufferModelPts.forward + BaseModel rescale, host pinned in/out"},
+                "d2h_bytes_per_step": d2h, "api": "ViewPipeline.submit(ZbufferModelPts.forward) + BaseModel rescale, host pinned in/out; the host waits for "
+                       "each step's pixels"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": rl,
         "lmconv_tokens_per_s": job_cells_sampled / (per_step["lmconv_tc_kernel"][0] * 1e-3),
         "lmconv_cells_per_s": job_cells_processed / (per_step["lmconv_tc_kernel"][0] * 1e-3),
         "lmconv_config3_tokens_per_s": 32 * 512 / (c3_ms * 1e-3),
         "ms_per_step_per_rank": [m / args.steps for m in ms_res_ranks],
+        "one_step_at_a_time": {"value": views_per_step * args.steps / (ms_serial * 1e-3), "unit": UNIT,
+                               "ms_per_step": ms_serial / args.steps,
+                               "note": "same model, ZbufferModelPts.forward called serially on the whole device (the latency of a step)"},
+        "sm_partition": {"sampler": n_small, "rest": n_big},
         "broadcast_ms": bcast_ms,
     }
     if world == 1 and not args.no_cpu_baseline:

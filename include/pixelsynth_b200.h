@@ -316,6 +316,20 @@ int ps_wedge_poll(unsigned int* info8_or_null);
 int ps_wedge_log(unsigned int* out, int max_words); /* developer aid: raw watchdog words incl. the waiter snapshot */
 void ps_wedge_reset(void);
 
+/* SM partitions for pipelined serving (no counterpart in the reference, which runs one batch at a time: this is the
+ * scheduling a B200 deployment adds around models/z_buffermodel.py:291-419).  The sampler launch is a latency-bound
+ * chain that keeps few SMs busy, so a serving loop keeps two batches in flight: batch k+1's
+ * sampler runs on a small partition while batch k's refinement decoder fills the rest.  ps_sm_partition_create splits
+ * the device's SMs into two disjoint CUDA green contexts (>= small_sms SMs, rounded up to the hardware granularity,
+ * and the remainder) and creates n_small_streams / n_big_streams non-blocking streams on them (cudaStream_t, written
+ * to the caller's arrays).  Kernels of this library launched on such a stream size their persistent grids to the
+ * partition (ps_stream_sm_count).  PS_EUNSUPPORTED when the driver has no green contexts.  The handle owns the
+ * contexts and streams; ps_sm_partition_destroy synchronises and releases them. */
+int ps_sm_partition_create(int device, int small_sms, int n_small_streams, void** small_streams, int n_big_streams,
+                           void** big_streams, int* small_count, int* big_count, void** handle);
+int ps_sm_partition_destroy(void* handle);
+int ps_stream_sm_count(void* stream);
+
 /* Per-kernel device timing for bench.py's roofline: while enabled, selected kernels  are bracketed by CUDA events on the launching stream.  ps_timing_collect(name, ...)
  * synchronises those events and returns the summed duration and launch count for `name`;
  * ps_timing_collect(NULL, ...) returns the sum over all names and releases the events. */

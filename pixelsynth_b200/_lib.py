@@ -45,6 +45,9 @@ SIGNATURES = {
     "ps_wedge_poll": (c_i, [c_p]),
     "ps_wedge_log": (c_i, [c_p, c_i]),
     "ps_wedge_reset": (None, []),
+    "ps_sm_partition_create": (c_i, [c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
+    "ps_sm_partition_destroy": (c_i, [c_p]),
+    "ps_stream_sm_count": (c_i, [c_p]),
     "ps_launch_count": (ctypes.c_longlong, []),
     "ps_launch_count_reset": (None, []),
     "ps_timing_enable": (None, [c_i]),

@@ -1,4 +1,5 @@
 // Library-wide C-ABI bookkeeping: version, error strings, launch counter.
+#include <cuda.h>
 #include <string.h>
 
 #include <mutex>
@@ -22,6 +23,50 @@ void timing_begin(const char* name, cudaStream_t stream) {
   if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
   cudaEventRecord(t.a, stream);
   g_timed.push_back(t);
+}
+
+int stream_sms(cudaStream_t stream) {
+  static thread_local int dev_cached = -1, dev_sms = 148;
+  static thread_local cudaStream_t last_stream = nullptr;
+  static thread_local int last_sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return dev_sms;
+  if (dev != dev_cached) {
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev);
+    dev_cached = dev;
+    last_sms = 0;
+  }
+  if (!stream || stream == cudaStreamLegacy || stream == cudaStreamPerThread) return dev_sms;
+  if (last_sms && stream == last_stream) return last_sms;
+  typedef CUresult (*GetGreenFn)(CUstream, CUgreenCtx*);
+  typedef CUresult (*GetResFn)(CUgreenCtx, CUdevResource*, CUdevResourceType);
+  static GetGreenFn get_green = nullptr;
+  static GetResFn get_res = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    void *a = nullptr, *b = nullptr;
+    cudaDriverEntryPointQueryResult qa, qb;
+    if (cudaGetDriverEntryPoint("cuStreamGetGreenCtx", &a, cudaEnableDefault, &qa) == cudaSuccess &&
+        qa == cudaDriverEntryPointSuccess &&
+        cudaGetDriverEntryPoint("cuGreenCtxGetDevResource", &b, cudaEnableDefault, &qb) == cudaSuccess &&
+        qb == cudaDriverEntryPointSuccess) {
+      get_green = (GetGreenFn)a;
+      get_res = (GetResFn)b;
+    }
+    looked = true;
+  }
+  int n = dev_sms;
+  if (get_green) {
+    CUgreenCtx g = nullptr;
+    CUdevResource r;
+    memset(&r, 0, sizeof(r));
+    if (get_green((CUstream)stream, &g) == CUDA_SUCCESS && g && get_res(g, &r, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+        r.sm.smCount > 0)
+      n = (int)r.sm.smCount < dev_sms ? (int)r.sm.smCount : dev_sms;
+  }
+  last_stream = stream;
+  last_sms = n;
+  return n;
 }
 
 unsigned int* wedge_host_words() {
@@ -52,6 +97,21 @@ int wedge_check(const char* func) {
 void timing_end(cudaStream_t stream) {
   if (!g_timed.empty()) cudaEventRecord(g_timed.back().b, stream);
 }
+// ---- SM partitions (CUDA green contexts) --------------------------------------------------------------------------
+struct SmPartition {
+  CUgreenCtx ctx[2];
+  std::vector<cudaStream_t> streams;
+};
+
+template <class F>
+static bool driver_fn(const char* name, F* out) {
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+  *out = (F)sym;
+  return true;
+}
+
 }  // namespace ps
 
 extern "C" {
@@ -94,6 +154,84 @@ void ps_wedge_reset(void) {
   unsigned int* w = ps::wedge_host_words();
   if (w) memset(w, 0, ps::PS_WEDGE_WORDS * sizeof(unsigned int));
 }
+
+int ps_sm_partition_create(int device, int small_sms, int n_small_streams, void** small_streams, int n_big_streams,
+                           void** big_streams, int* small_count, int* big_count, void** handle) {
+  PS_CHECK_ARG(device >= 0 && small_sms > 0 && n_small_streams >= 0 && n_big_streams >= 0 && handle);
+  PS_CHECK_ARG((n_small_streams == 0 || small_streams) && (n_big_streams == 0 || big_streams));
+  CUresult (*dev_get)(CUdevice*, int) = nullptr;
+  CUresult (*dev_res)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*gen_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*ctx_create)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*stream_create)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  CUresult (*ctx_destroy)(CUgreenCtx) = nullptr;
+  if (!ps::driver_fn("cuDeviceGet", &dev_get) || !ps::driver_fn("cuDeviceGetDevResource", &dev_res) ||
+      !ps::driver_fn("cuDevSmResourceSplitByCount", &split) || !ps::driver_fn("cuDevResourceGenerateDesc", &gen_desc) ||
+      !ps::driver_fn("cuGreenCtxCreate", &ctx_create) || !ps::driver_fn("cuGreenCtxStreamCreate", &stream_create) ||
+      !ps::driver_fn("cuGreenCtxDestroy", &ctx_destroy))
+    return ps::fail(PS_EUNSUPPORTED, "%s: this driver has no green-context entry points%s", __func__, "");
+  PS_CUDA(cudaSetDevice(device));
+  PS_CUDA(cudaFree(0));  // the primary context exists
+  CUdevice dev;
+  CUdevResource all, part, rest;
+  unsigned int groups = 1;
+  memset(&all, 0, sizeof(all));
+  memset(&part, 0, sizeof(part));
+  memset(&rest, 0, sizeof(rest));
+  if (dev_get(&dev, device) != CUDA_SUCCESS || dev_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS)
+    return ps::fail(PS_ECUDA, "%s: cuDeviceGetDevResource failed%s", __func__, "");
+  if ((unsigned)small_sms >= all.sm.smCount)
+    return ps::fail(PS_EINVAL, "%s: small_sms leaves nothing of the device's SMs%s", __func__, "");
+  if (split(&part, &groups, &all, &rest, 0, (unsigned)small_sms) != CUDA_SUCCESS || groups != 1 || rest.sm.smCount == 0)
+    return ps::fail(PS_ECUDA, "%s: cuDevSmResourceSplitByCount failed%s", __func__, "");
+  ps::SmPartition* sp = new ps::SmPartition();
+  sp->ctx[0] = sp->ctx[1] = nullptr;
+  CUdevResource* res[2] = {&part, &rest};
+  void** outs[2] = {small_streams, big_streams};
+  const int counts[2] = {n_small_streams, n_big_streams};
+  bool ok = true;
+  for (int i = 0; i < 2 && ok; ++i) {
+    CUdevResourceDesc desc;
+    ok = gen_desc(&desc, res[i], 1) == CUDA_SUCCESS && ctx_create(&sp->ctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS;
+    for (int k = 0; k < counts[i] && ok; ++k) {
+      CUstream st = nullptr;
+      ok = stream_create(&st, sp->ctx[i], CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS;
+      if (ok) {
+        sp->streams.push_back((cudaStream_t)st);
+        outs[i][k] = (void*)st;
+      }
+    }
+  }
+  if (!ok) {
+    for (cudaStream_t st : sp->streams) cudaStreamDestroy(st);
+    for (int i = 0; i < 2; ++i)
+      if (sp->ctx[i]) ctx_destroy(sp->ctx[i]);
+    delete sp;
+    return ps::fail(PS_ECUDA, "%s: creating the green contexts / streams failed%s", __func__, "");
+  }
+  if (small_count) *small_count = (int)part.sm.smCount;
+  if (big_count) *big_count = (int)rest.sm.smCount;
+  *handle = sp;
+  return PS_OK;
+}
+
+int ps_sm_partition_destroy(void* handle) {
+  if (!handle) return PS_OK;
+  ps::SmPartition* sp = (ps::SmPartition*)handle;
+  CUresult (*ctx_destroy)(CUgreenCtx) = nullptr;
+  for (cudaStream_t st : sp->streams) {
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  }
+  if (ps::driver_fn("cuGreenCtxDestroy", &ctx_destroy))
+    for (int i = 0; i < 2; ++i)
+      if (sp->ctx[i]) ctx_destroy(sp->ctx[i]);
+  delete sp;
+  return PS_OK;
+}
+
+int ps_stream_sm_count(void* stream) { return ps::stream_sms((cudaStream_t)stream); }
 
 void ps_timing_enable(int on) { ps::g_timing_on = on; }
 

@@ -11,6 +11,9 @@ namespace ps {
 
 extern thread_local char g_err_detail[512];
 extern thread_local long long g_launches;
+// SMs the stream's kernels may occupy: the device's count, or the partition's when the stream belongs to a CUDA green
+// context (cuGreenCtxStreamCreate) -- persistent kernels size their grid with this.
+int stream_sms(cudaStream_t stream);
 
 inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
   snprintf(g_err_detail, sizeof(g_err_detail), fmt, a, b);

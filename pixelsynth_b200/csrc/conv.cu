@@ -773,14 +773,13 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   // groups of two tiles share every weight tile: needs four accumulator buffers (4 x BN <= 512 TMEM columns); it
   // only pays when there are more tiles than SMs (otherwise it would just idle half of them)
   static thread_local int attr_dev = -1;
-  static thread_local int sms = 148;
   int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
   if (attr_dev != dev) {
     PS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr_dev = dev;
   }
+  const int sms = stream_sms((cudaStream_t)stream);  // the whole device, or the stream's green-context partition
   p.tiles_spatial = p.tiles_x * p.tiles_y * tiles_n;
   p.total_tiles = p.tiles_spatial * (d->cout_pad / BN);
   p.tpg = (halo && BN <= 128 && !(dbg & 1) && p.total_tiles >= 2 * sms) ? 2 : 1;

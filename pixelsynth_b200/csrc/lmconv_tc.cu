@@ -1494,9 +1494,9 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   p.trace = g_tc_trace;
   p.debug = getenv("PS_TC_DEBUG") ? atoi(getenv("PS_TC_DEBUG")) : 0;
 
-  int dev = 0, sms = 148;
+  int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
-  PS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = stream_sms((cudaStream_t)stream);
   // tiles in level order: a level's rows are split evenly over its tiles
   std::vector<Tile> tiles;
   const int exp_bits = getenv("PS_TC_EXP") ? atoi(getenv("PS_TC_EXP")) : 0;  // developer aid: scheduling experiments

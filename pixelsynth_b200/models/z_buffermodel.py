@@ -84,6 +84,7 @@ class ZbufferModelPts(nn.Module):
         self.obs = [3, 32, 32]
         self.ranker = None
         self._bg_pin = None
+        self.sampler_stream = None   # optional side stream for the sampler launch (pipelined serving)
 
     # -- z_buffermodel.py:120-184 ---------------------------------------------------------------
     def process_batch(self, batch):
@@ -160,7 +161,7 @@ class ZbufferModelPts(nn.Module):
         T = float(_get(self.opt, "temperature", 1.0))
         if n == 1:
             u = uniforms if uniforms is not None else self._sampler_uniforms(0, B)
-            sampled = self.outpaint2.sample(codes, order, words, sample_mask, u, T, prepared=prepared)
+            sampled = self._sample(codes, order, words, sample_mask, u, T, prepared)
             ar_sample = self.vqvae.decode_code(sampled)
             combined = self.get_combined(gen_fs, ar_sample, background_mask)
             return self.projector.forward(combined, background_mask, noise)
@@ -182,6 +183,18 @@ class ZbufferModelPts(nn.Module):
         best = int(self.ranker(imgs, input_img)) if self.ranker is not None else 0
         self.last_best = best
         return imgs[best]
+
+    def _sample(self, codes, order, words, sample_mask, u, T, prepared=None):
+        side = self.sampler_stream
+        if side is None:
+            return self.outpaint2.sample(codes, order, words, sample_mask, u, T, prepared=prepared)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = self.outpaint2.sample(codes, order, words, sample_mask, u, T, prepared=prepared)
+        cur.wait_stream(side)
+        out.record_stream(cur)
+        return out
 
     def _default_ranker(self):
         """The reference ranks with BaseModel.netD and ZbufferModelPts.classifier (demo.py:233-243 loads its places365

@@ -304,3 +304,39 @@ def test_num_samples_ranking_matches_oracle_scores(oracle):
             min(abs(a - b) for i, a in enumerate(e_ref) for b in e_ref[i + 1:]) > 0.1:
         assert m.last_best == ranking.rank_fusion(d_ref, e_ref)
     assert torch.equal(out["PredImg"].cpu(), cands[m.last_best])     # the folded batch equals the per-candidate calls
+
+
+@pytest.mark.parametrize("partition", [True, False])
+def test_view_pipeline_two_in_flight_equals_serial(model, partition):
+    """pixelsynth_b200.pipeline.ViewPipeline: two batches in flight, the sampler on its own SM partition (CUDA green
+    contexts), give bit-identical images to one forward at a time -- five different batches, different views."""
+    from pixelsynth_b200 import _lib
+    from pixelsynth_b200.pipeline import ViewPipeline
+
+    B = 6
+    g = torch.Generator().manual_seed(11)
+    jobs = []
+    for i in range(5):
+        jobs.append((make_batch(B, "translate" if i % 2 == 0 else "rotate", seed=i),
+                     torch.randn(16, B, 20, generator=g), torch.rand(B, 1024, generator=g)))
+    want = []
+    for b, n, u in jobs:
+        want.append(model.forward(b, noise=n, uniforms=u)[1]["PredImg"].clone())
+    torch.cuda.synchronize()
+    with ViewPipeline(model, depth=2, sampler_sms=24, partition=partition) as pipe:
+        if partition:
+            ns, nb = pipe.sm_counts
+            assert ns >= 24 and ns + nb == torch.cuda.get_device_properties(0).multi_processor_count
+            L = _lib.lib()
+            assert L.ps_stream_sm_count(pipe.sampler_stream.cuda_stream) == ns
+            assert L.ps_stream_sm_count(pipe.streams[0].cuda_stream) == nb
+            assert L.ps_stream_sm_count(torch.cuda.current_stream().cuda_stream) == ns + nb
+        tickets = [pipe.submit(b, noise=n, uniforms=u) for b, n, u in jobs]
+        got = [pipe.result(t)[1]["PredImg"] for t in tickets]
+        for w, x in zip(want, got):
+            assert torch.equal(w, x)
+        # the generator form, and the `then` hook (runs on the slot's stream)
+        outs = list(pipe.map([j[0] for j in jobs[:3]], noise=jobs[0][1], uniforms=jobs[0][2]))
+        assert torch.equal(outs[0][1]["PredImg"], want[0])
+        t = pipe.submit(jobs[1][0], then=lambda loss, o: (0.5 * o["PredImg"] + 0.5).cpu(), noise=jobs[1][1], uniforms=jobs[1][2])
+        assert torch.equal(pipe.result(t), (0.5 * want[1] + 0.5).cpu())

@@ -47,8 +47,8 @@ UNIT = "views/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64,
                     help="images (= views) per step per GPU (BASELINE configs[3]: batch 64).  The sampler's serial levels "
@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--num_split", type=int, default=2, help="scene sweep splits per direction (scripts/demo_scene.sh: 32)")
     ap.add_argument("--cpu-tokens", type=int, default=16, help="sampler tokens timed per step for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=3,
                     help="batches in flight per GPU (pixelsynth_b200.pipeline.ViewPipeline); 1 = one forward at a time")
     ap.add_argument("--sampler-sms", type=int, default=24, help="SMs of the sampler's green-context partition (in-flight > 1)")
     return ap.parse_args()
@@ -500,14 +500,14 @@ def main():
     d2h = h_out.numel() * 4
 
     # ---- per-kernel device time over the same step (CUDA events recorded by the library on the launching stream) ----
-    step_resident()
-    drain()
+    # One step at a time on the whole device: with steps in flight an event-bracketed duration would include the time a
+    # kernel's CTAs queue behind the other step's kernels, so the kernels are timed where their durations are their own.
+    step_serial()
     torch.cuda.synchronize()
     _lib.kernel_time_ms(None)
     L.ps_timing_enable(1)
     for _ in range(args.steps):
-        step_resident()
-    drain()
+        step_serial()
     torch.cuda.synchronize()
     L.ps_timing_enable(0)
     kt = {n: _lib.kernel_time_ms(n) for n in ("fine_kernel", "fine_big_kernel", "conv_igemm_kernel", "lmconv_tc_kernel")}
@@ -630,21 +630,15 @@ def main():
     except Exception:
         pass
     n_small, n_big = pipe.sm_counts if pipe.sm_counts else (0, 0)
+    serial_step_ms = ms_serial / args.steps
     for k, v in rl.items():
         v["frac"] = v["achieved"] / v["peak"]
-        v["share_of_step"] = 0.0 if ("maps" in k or "config 3" in k) else v["ms_per_step"] / step_ms
-        if n_big and k in ("conv_igemm_kernel", "lmconv_tc_kernel"):
-            # inside the timed step the kernel is confined to its partition and runs beside the other one: `frac` stays
-            # against the WHOLE device's measured peak (a kernel on 124 of 148 SMs cannot exceed 0.84); shares of
-            # concurrent kernels add up to more than 1
-            v["sms"] = n_big if k == "conv_igemm_kernel" else n_small
-            v["frac_of_partition_peak"] = v["frac"] * (n_small + n_big) / v["sms"]
-    # dominant = the kernel holding the largest share of the device (duration x the SMs it may occupy): with two steps in
-    # flight the sampler's launch is long but confined to its small partition
-    dom = max((k for k in rl if "maps" not in k and "config 3" not in k),
-              key=lambda k: rl[k]["ms_per_step"] * rl[k].get("sms", n_small + n_big or 1))
+        v["share_of_step"] = 0.0 if ("maps" in k or "config 3" in k) else v["ms_per_step"] / serial_step_ms
+    dom = max((k for k in rl if "maps" not in k and "config 3" not in k), key=lambda k: rl[k]["ms_per_step"])
     roof = dict(rl[dom])
-    roof.update({"kernel": dom, "traffic": traffic.get(dom), "traffic_source": traffic.get("source"), "peak_source": peak_src})
+    roof.update({"timed_in": "the one-step-at-a-time pass of this run (whole device; `one_step_at_a_time`): kernel durations "
+                             "are unambiguous there, while steps in flight queue behind each other's kernels",
+                 "kernel": dom, "traffic": traffic.get(dom), "traffic_source": traffic.get("source"), "peak_source": peak_src})
     views_per_step = B * world
     line = {
         "metric": METRIC, "value": views_per_step * args.steps / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- novel views/sec (256x256) of the pixelsynth_b200 hot path, with rooflines and a CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--view V]
+                    [--in-flight D] [--sampler-sms S] [--workload views|scene]
 
 One JSON line on stdout from rank 0 (contract in DESIGN.md section 7).
   workload  = BASELINE.json configs[1]: the demo path `ZbufferModelPts.forward` (models/z_buffermodel.py:291-419) --
@@ -9,11 +10,18 @@ One JSON line on stdout from rank 0 (contract in DESIGN.md section 7).
               VQ-VAE-2 decode -> refinement decoder -- on synthetic 256x256 images, one novel view per image, batched
               B images per step (the path is embarrassingly parallel over images).  Seeded random weights of the
               reference's architecture (no checkpoint is reachable offline).
-  value     = views/s with the inputs resident in HBM; CUDA events on the launching stream; max over ranks.
-  e2e       = views/s through BaseModel.__call__ (models/base_model.py:93-103) with HOST pinned inputs: H2D of
-              images + cameras and D2H of PredImg inside the timed region.
+  value     = views/s with the inputs resident in HBM; the K steps go through pixelsynth_b200.pipeline.ViewPipeline
+              with `--in-flight` batches in flight (the sampler of step k+1 on its own SM partition beside the decoder
+              of step k) and all complete inside the timed region; CUDA events; max over ranks.
+              `one_step_at_a_time` = the same model called serially on the whole device (the latency of a step).
+  e2e       = views/s through ViewPipeline.submit(ZbufferModelPts.forward) + BaseModel's rescale
+              (models/base_model.py:93-103) with HOST pinned inputs: H2D of images + cameras and D2H of PredImg every
+              step, the host waiting for each step's pixels.
   roofline  = the dominant kernel of the step (by summed device time, measured with CUDA events the library records
-              on the launching stream); `rooflines` lists splat (HBM), sampler and convolutions (tensor).
+              on the launching stream during the one-step-at-a-time pass of the same run); `rooflines` lists splat
+              (HBM; also with maps emitted on the U-Net's and on SURVEY 8d's uniform depth), sampler (step and
+              BASELINE config 3) and convolutions (tensor).
+  --workload scene = BASELINE configs[4]: batched gen_scene sweeps (models/z_buffermodel.py:421-592).
   cpu_baseline / --impl reference = the CPU oracle of the same path (fp32 torch restatement of the reference's
               modules + the C splat oracle); the sampler is timed reference-style (one full forward per token,
               models/lmconv/sample.py:54-66) on a few tokens and extrapolated linearly -- stated in `sample`.

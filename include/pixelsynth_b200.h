@@ -292,9 +292,11 @@ int ps_lmconv_levels_host(const int* order, const uint16_t* words, const uint8_t
                           ps_lmconv_row* rows_out, int* level_offsets, int max_levels, int* n_levels,
                           int* first_b_level);
 
-/* Device: runs all levels in one launch on `stream`.  Exception to the "nothing synchronises" convention above, for
- * round 1: the call waits for `stream` to drain after uploading its tile table and before the launch (an intermittent
- * launch failure at batch 128 whose cause is open never appeared when this kernel ran serialised).  codes (B,1024) i64: in = known codes, out = sampled cells
+/* Device: runs all levels in one launch on `stream`; nothing synchronises (the tile table goes through a pinned
+ * staging buffer of the calling thread; the call waits only for the PREVIOUS call's copy out of that buffer).  Levels at
+ * or after first_b_level are split into parallel halo tiles and short chain tiles; the grid is
+ * one CTA per tile in dependency order.  Fails with PS_ECUDA if an earlier tensor-core launch wedged (ps_wedge_poll).
+ * codes (B,1024) i64: in = known codes, out = sampled cells
  * filled; uniforms (B,stride) f32: the k-th sampled cell (in generation order) of image b takes the first class whose
  * cumulative softmax(logits/temperature) exceeds uniforms[b][k]; logits_out (B,1024,512) f32 or NULL receives the
  * logits of rows flagged bit17; cache: ps_lmconv_tc_cache_bytes(B) bytes of device scratch. */

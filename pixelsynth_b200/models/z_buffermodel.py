@@ -13,9 +13,12 @@ Weights: a state dict with the reference's key names (`pts_regressor.*`, `vqvae.
 `module.` / `model.module.` prefixes of DataParallel checkpoints are stripped, demo.py:202-229).  Without a state
 dict the networks are random-initialised from opt.seed (pixelsynth_b200/synthetic.py): no checkpoint of the
 reference is reachable offline.
-num_samples > 1 (z_buffermodel.py:244-276): `ranker(imgs, input_img) -> index` picks the candidate --
-pixelsynth_b200.ranking.Ranker reproduces the reference's rank fusion around injected discriminator / places365
-scorers (their weights are not reachable offline); without a ranker sample 0 is kept.
+num_samples > 1 (z_buffermodel.py:244-276): all candidates are ONE batch (one sampler launch, one decode, one
+refinement pass) and `ranker(imgs, input_img) -> index` picks one.  The default ranker is built lazily from the state
+dict's `netD.` / `classifier.` entries (seeded random when absent): pixelsynth_b200.ranking.GpuRanker =
+nets.MultiscaleDiscriminatorB200 (D_Fake) + nets.ResNet18B200 (places365 entropy) + the reference's rank fusion.
+forward_scene (z_buffermodel.py:421-592) takes batches of images (BASELINE config 5).
+`sampler_stream` (optional) moves the sampler launch to a side stream: pixelsynth_b200.pipeline.ViewPipeline.
 Stochastic elements are explicit: `noise` (decoder, 16 x (B,20)) and `uniforms` (sampler) can be injected; when
 absent they are drawn from torch generators seeded as the reference seeds its sampler (sample.py:14-16)."""
 import math

@@ -48,6 +48,54 @@ struct ResampleOut {
   int per_sample, act, cstride, coffset;
 };
 
+// y = act(v * scale + shift) of one (pixel, 8-channel group) into up to two NHWC bf16 outputs.  The activation is
+// selected once per group (a switch around the 8-channel loop, not inside it): these kernels are instruction-bound.
+template <int ACT>
+__device__ __forceinline__ void store_group(const float (&t)[8], __nv_bfloat16* dst) {
+  float y[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = ew_act(t[j], ACT);
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(y[4], y[5]), h3 = __floats2bfloat162_rn(y[6], y[7]);
+  uint4 w;
+  w.x = *reinterpret_cast<uint32_t*>(&h0);
+  w.y = *reinterpret_cast<uint32_t*>(&h1);
+  w.z = *reinterpret_cast<uint32_t*>(&h2);
+  w.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = w;
+}
+
+__device__ __forceinline__ void resample_store(const float (&v)[8], int n, int g, int oy, int ox, int Ho, int Wo, int C,
+                                               const ResampleOut& o0, const ResampleOut& o1) {
+  const ResampleOut* outs[2] = {&o0, &o1};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const ResampleOut& o = *outs[k];
+    if (!o.ptr) continue;
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[j];
+    if (o.scale) {
+      const float4* sc = reinterpret_cast<const float4*>(o.scale + (o.per_sample ? (size_t)n * C : 0) + g * 8);
+      const float4 a = __ldg(sc), c = __ldg(sc + 1);
+      t[0] *= a.x, t[1] *= a.y, t[2] *= a.z, t[3] *= a.w, t[4] *= c.x, t[5] *= c.y, t[6] *= c.z, t[7] *= c.w;
+    }
+    if (o.shift) {
+      const float4* sh = reinterpret_cast<const float4*>(o.shift + (o.per_sample ? (size_t)n * C : 0) + g * 8);
+      const float4 a = __ldg(sh), c = __ldg(sh + 1);
+      t[0] += a.x, t[1] += a.y, t[2] += a.z, t[3] += a.w, t[4] += c.x, t[5] += c.y, t[6] += c.z, t[7] += c.w;
+    }
+    __nv_bfloat16* dst = o.ptr + (((size_t)n * Ho + oy) * Wo + ox) * o.cstride + o.coffset + g * 8;
+    switch (o.act) {
+      case PS_ACT_RELU: store_group<PS_ACT_RELU>(t, dst); break;
+      case PS_ACT_LEAKY02: store_group<PS_ACT_LEAKY02>(t, dst); break;
+      case PS_ACT_TANH: store_group<PS_ACT_TANH>(t, dst); break;
+      case PS_ACT_ELU: store_group<PS_ACT_ELU>(t, dst); break;
+      default: store_group<PS_ACT_NONE>(t, dst); break;
+    }
+  }
+}
+
 // mode 0: identity, 1: AvgPool2d(3, stride 2, pad 1, count_include_pad), 2: bilinear x2 (align_corners=False),
 // 3: avg_pool2d(3, 2, 1, count_include_pad=False) (the discriminator's downsample, discriminators.py:170-177),
 // 4: MaxPool2d(3, 2, 1) (torchvision resnet18).
@@ -121,37 +169,60 @@ __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __re
     accum(y1, x0, ly * (1.0f - lx));
     accum(y1, x1, ly * lx);
   }
-  const ResampleOut* outs[2] = {&o0, &o1};
+  resample_store(v, n, g, oy, ox, Ho, Wo, C, o0, o1);
+}
+
+// Bilinear x2 (PyTorch upsample_bilinear2d, align_corners=False) with one thread per INPUT cell (i, j) in
+// [-1, H-1] x [-1, W-1] and 8-channel group: the four inputs (i, j), (i, j+1), (i+1, j), (i+1, j+1) (clamped) are loaded
+// once and give the up to four outputs (2i+1 | 2i+2, 2j+1 | 2j+2) -- a quarter of the loads and address arithmetic of
+// the one-thread-per-output kernel.  Per output the weights and the order of the four terms are exactly those of
+// resample_kernel's mode 2 (src = (dst + 0.5) / 2 - 0.5 clamped at 0), so the results are bit-identical.
+__global__ void __launch_bounds__(256, 4) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int N, int H, int W, int C,
+                                                         int in_cstride, ResampleOut o0, ResampleOut o1) {
+  const unsigned groups = (unsigned)C >> 3;
+  const unsigned ix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ix >= (unsigned)(W + 1) * groups) return;
+  const int jj = (int)(ix / groups);
+  const int g = (int)(ix - (unsigned)jj * groups);
+  const int j = jj - 1, i = (int)blockIdx.y - 1;
+  const int n = blockIdx.z;
+  const int r0 = max(i, 0), r1 = min(i + 1, H - 1), c0 = max(j, 0), c1 = min(j + 1, W - 1);
+  float f[4][8];
+  {
+    const int rr[4] = {r0, r0, r1, r1}, cc[4] = {c0, c1, c0, c1};
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const ResampleOut& o = *outs[k];
-    if (!o.ptr) continue;
-    const float* sc = o.scale ? o.scale + (o.per_sample ? (size_t)n * C : 0) + g * 8 : nullptr;
-    const float* sh = o.shift ? o.shift + (o.per_sample ? (size_t)n * C : 0) + g * 8 : nullptr;
-    float y[8], s8[8], h8[8];
-    if (sc) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(sc)), c = __ldg(reinterpret_cast<const float4*>(sc) + 1);
-      s8[0] = a.x, s8[1] = a.y, s8[2] = a.z, s8[3] = a.w, s8[4] = c.x, s8[5] = c.y, s8[6] = c.z, s8[7] = c.w;
-    }
-    if (sh) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(sh)), c = __ldg(reinterpret_cast<const float4*>(sh) + 1);
-      h8[0] = a.x, h8[1] = a.y, h8[2] = a.z, h8[3] = a.w, h8[4] = c.x, h8[5] = c.y, h8[6] = c.z, h8[7] = c.w;
-    }
+    for (int t = 0; t < 4; ++t) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * H + rr[t]) * W + cc[t]) * in_cstride + g * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = v[j];
-      if (sc) t *= s8[j];
-      if (sh) t += h8[j];
-      y[j] = ew_act(t, o.act);
+      for (int q = 0; q < 4; ++q) {
+        const float2 v2 = __bfloat1622float2(h[q]);
+        f[t][2 * q] = v2.x;
+        f[t][2 * q + 1] = v2.y;
+      }
     }
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(y[0], y[1]), h1 = __floats2bfloat162_rn(y[2], y[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(y[4], y[5]), h3 = __floats2bfloat162_rn(y[6], y[7]);
-    uint4 w;
-    w.x = *reinterpret_cast<uint32_t*>(&h0);
-    w.y = *reinterpret_cast<uint32_t*>(&h1);
-    w.z = *reinterpret_cast<uint32_t*>(&h2);
-    w.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(o.ptr + (((size_t)n * Ho + oy) * Wo + ox) * o.cstride + o.coffset + g * 8) = w;
+  }
+  const int Ho = 2 * H, Wo = 2 * W;
+#pragma unroll
+  for (int dy = 1; dy <= 2; ++dy) {
+    const int oy = 2 * i + dy;
+    if (oy < 0 || oy >= Ho) continue;
+    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.0f);
+    const float ly = sy - (float)(int)sy;
+#pragma unroll
+    for (int dx = 1; dx <= 2; ++dx) {
+      const int ox = 2 * j + dx;
+      if (ox < 0 || ox >= Wo) continue;
+      const float sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.0f);
+      const float lx = sx - (float)(int)sx;
+      const float w[4] = {(1.0f - ly) * (1.0f - lx), (1.0f - ly) * lx, ly * (1.0f - lx), ly * lx};
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] += w[t] * f[t][q];
+      resample_store(v, n, g, oy, ox, Ho, Wo, C, o0, o1);
+    }
   }
 }
 
@@ -181,44 +252,109 @@ __global__ void noise_affine_kernel(const float* __restrict__ z, int N, int Z, c
 }
 
 // Nearest codebook entry: argmax_j -(|x|^2 - 2 x.E_j + |E_j|^2)  (vqvae.py:42-48).  x: (N, D, HW) fp32 (NCHW),
-// embed: (D, J).  One warp per pixel; ties resolve to the smallest j (torch.max returns the first maximum).
+// embed: (D, J).  Ties resolve to the smallest j (torch.max returns the first maximum).
+// One CTA per 32 pixels: their D-vectors sit in shared memory, a thread owns codes tid, tid + 256, ... and walks the
+// codebook once for all 32 pixels (one coalesced load per (d, code) instead of one per (d, code, pixel)); per pixel the
+// sums run over d in the same order as a plain loop would, so the scores do not depend on the tiling.
+constexpr int VQ_PX = 32;
+constexpr int VQ_MAXD = 64;
 __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict__ x, int N, int D, int HW,
                                                         const float* __restrict__ embed, int J,
                                                         long long* __restrict__ ids) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N * HW) return;
-  const int n = warp / HW, r = warp - n * HW;
-  const float* xp = x + (size_t)n * D * HW + r;
-  float x2 = 0.0f;
-  for (int d = 0; d < D; ++d) {
-    const float v = xp[(size_t)d * HW];
-    x2 += v * v;
+  __shared__ __align__(16) float xs[VQ_MAXD][VQ_PX];
+  __shared__ float x2s[VQ_PX];
+  __shared__ float wbest[8][VQ_PX];
+  __shared__ int wj[8][VQ_PX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long total = (long long)N * HW;
+  const long long base = (long long)blockIdx.x * VQ_PX;
+  for (int i = tid; i < D * VQ_PX; i += 256) {
+    const int d = i / VQ_PX, p = i - d * VQ_PX;
+    const long long gp = base + p;
+    float v = 0.0f;
+    if (gp < total) {
+      const long long n = gp / HW, r = gp - n * HW;
+      v = x[(size_t)n * D * HW + (size_t)d * HW + r];
+    }
+    xs[d][p] = v;
   }
-  float best = -INFINITY;
-  int bj = 0x7fffffff;
-  for (int j = lane; j < J; j += 32) {
-    float dot = 0.0f, e2 = 0.0f;
+  __syncthreads();
+  if (tid < VQ_PX) {
+    float x2 = 0.0f;
+    for (int d = 0; d < D; ++d) x2 += xs[d][tid] * xs[d][tid];
+    x2s[tid] = x2;
+  }
+  __syncthreads();
+  float best[VQ_PX];
+  int bj[VQ_PX];
+#pragma unroll
+  for (int p = 0; p < VQ_PX; ++p) {
+    best[p] = -INFINITY;
+    bj[p] = 0x7fffffff;
+  }
+  for (int j = tid; j < J; j += 256) {
+    float dot[VQ_PX];
+#pragma unroll
+    for (int p = 0; p < VQ_PX; ++p) dot[p] = 0.0f;
+    float e2 = 0.0f;
     for (int d = 0; d < D; ++d) {
       const float e = embed[(size_t)d * J + j];
-      dot += xp[(size_t)d * HW] * e;
       e2 += e * e;
-    }
-    const float score = -(x2 - 2.0f * dot + e2);
-    if (score > best) {
-      best = score;
-      bj = j;
-    }
-  }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-    const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-    if (ob > best || (ob == best && oj < bj)) {
-      best = ob;
-      bj = oj;
+      for (int p4 = 0; p4 < VQ_PX / 4; ++p4) {
+        const float4 v = *reinterpret_cast<const float4*>(&xs[d][4 * p4]);
+        dot[4 * p4 + 0] += v.x * e;
+        dot[4 * p4 + 1] += v.y * e;
+        dot[4 * p4 + 2] += v.z * e;
+        dot[4 * p4 + 3] += v.w * e;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < VQ_PX; ++p) {
+      const float score = -(x2s[p] - 2.0f * dot[p] + e2);
+      if (score > best[p]) {  // j ascends within a thread: the first maximum stays
+        best[p] = score;
+        bj[p] = j;
+      }
     }
   }
-  if (lane == 0) ids[warp] = bj;
+  // per pixel: best over the warp's lanes, lane p keeps pixel p's; then over the 8 warps
+  float mine = -INFINITY;
+  int minej = 0x7fffffff;
+#pragma unroll
+  for (int p = 0; p < VQ_PX; ++p) {
+    float b = best[p];
+    int j = bj[p];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, b, off);
+      const int oj = __shfl_xor_sync(0xffffffffu, j, off);
+      if (ob > b || (ob == b && oj < j)) {
+        b = ob;
+        j = oj;
+      }
+    }
+    if (lane == p) {
+      mine = b;
+      minej = j;
+    }
+  }
+  wbest[warp][lane] = mine;
+  wj[warp][lane] = minej;
+  __syncthreads();
+  if (tid < VQ_PX && base + tid < total) {
+    float b = wbest[0][tid];
+    int j = wj[0][tid];
+    for (int w = 1; w < 8; ++w) {
+      const float ob = wbest[w][tid];
+      const int oj = wj[w][tid];
+      if (ob > b || (ob == b && oj < j)) {
+        b = ob;
+        j = oj;
+      }
+    }
+    ids[base + tid] = j;
+  }
 }
 
 // embed_code: ids (N*HW) -> NHWC bf16 (N*HW, D) from embed (D, J)
@@ -391,8 +527,14 @@ int ps_resample(const void* in, int N, int H, int W, int C, int in_cstride, int 
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
   if (total == 0) return PS_OK;
   dim3 grid((unsigned)(((size_t)Wo * (C / 8) + 255) / 256), (unsigned)Ho, (unsigned)N);
-  resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)in, N, H, W, C, in_cstride, mode, Ho, Wo, o[0], o[1]);
+  static const bool generic_up = getenv("PS_UPSAMPLE_GENERIC") != nullptr;  // developer A/B switch
+  if (mode == 2 && !generic_up) {
+    dim3 grid2((unsigned)(((size_t)(W + 1) * (C / 8) + 255) / 256), (unsigned)(H + 1), (unsigned)N);
+    upsample2x_kernel<<<grid2, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, H, W, C, in_cstride, o[0], o[1]);
+  } else {
+    resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)in, N, H, W, C, in_cstride, mode, Ho, Wo, o[0], o[1]);
+  }
   PS_LAUNCHED();
   return PS_OK;
 }
@@ -430,9 +572,10 @@ int ps_noise_affine(const float* z, int N, int Z, const float* Wg, const float* 
 
 int ps_vq_argmin(const float* x, int N, int D, int HW, const float* embed, int J, long long* ids, void* stream) {
   PS_CHECK_ARG(x && embed && ids && N >= 0 && D >= 1 && HW >= 1 && J >= 1);
-  const size_t warps = (size_t)N * HW;
-  if (warps == 0) return PS_OK;
-  vq_argmin_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, N, D, HW, embed, J, ids);
+  PS_CHECK_ARG(D <= VQ_MAXD);
+  const size_t pixels = (size_t)N * HW;
+  if (pixels == 0) return PS_OK;
+  vq_argmin_kernel<<<(unsigned)((pixels + VQ_PX - 1) / VQ_PX), 256, 0, (cudaStream_t)stream>>>(x, N, D, HW, embed, J, ids);
   PS_LAUNCHED();
   return PS_OK;
 }

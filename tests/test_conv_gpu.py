@@ -131,3 +131,38 @@ def test_activations_fp32_only(cv):
     cv.conv_igemm(cv.to_nhwc_bf16(x.cuda()), pc, [cv.Out(None, "sigmoid_affine")], out_f32=o32, act_param=(9.5, 0.5))
     torch.cuda.synchronize()
     close(o32.cpu(), ref, 2e-3)
+
+
+@pytest.mark.parametrize("mode,shape", [("bilinear", (2, 5, 7, 16)), ("bilinear", (3, 16, 16, 64)), ("bilinear", (1, 1, 1, 8)),
+                                        ("avgpool", (2, 9, 6, 16)), ("avgpool_nopad", (2, 8, 8, 8)), ("maxpool", (1, 7, 7, 8))])
+def test_resample_modes_against_torch(mode, shape):
+    """ps_resample (nn.Upsample(bilinear) / nn.AvgPool2d(3,2,1) of blocks.py:46-48, the discriminator's and resnet18's
+    pools) against torch on the same bf16 inputs, fp32 arithmetic, one bf16 rounding at the end; the second output
+    carries the per-sample affine + ReLU the decoder fuses here."""
+    import torch.nn.functional as F
+    from pixelsynth_b200 import nets
+    from pixelsynth_b200.conv import Out
+
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda()
+    scale = (torch.rand(n, c, generator=g) + 0.5).cuda()
+    shift = torch.randn(n, c, generator=g).cuda()
+    xf = x.float().permute(0, 3, 1, 2)
+    if mode == "bilinear":
+        ref = F.interpolate(xf, scale_factor=2, mode="bilinear", align_corners=False)
+    elif mode == "avgpool":
+        ref = F.avg_pool2d(xf, 3, 2, 1)
+    elif mode == "avgpool_nopad":
+        ref = F.avg_pool2d(xf, 3, 2, 1, count_include_pad=False)
+    else:
+        ref = F.max_pool2d(xf, 3, 2, 1)
+    ho, wo = ref.shape[2:]
+    o0 = torch.empty(n, ho, wo, c, dtype=torch.bfloat16, device="cuda")
+    o1 = torch.empty_like(o0)
+    nets.resample(x, mode, Out(o0), Out(o1, "relu", scale, shift, per_sample=True))
+    ref1 = torch.relu(ref * scale[:, :, None, None] + shift[:, :, None, None])
+    for got, want in ((o0, ref), (o1, ref1)):
+        got = got.float().permute(0, 3, 1, 2)
+        err = (got - want).abs()
+        assert (err <= 2.0 ** -7 * want.abs() + 1e-6).all(), float(err.max())   # within one bf16 rounding of fp32

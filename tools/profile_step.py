@@ -17,7 +17,7 @@ from pixelsynth_b200.models.z_buffermodel import ZbufferModelPts  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 dev = torch.device("cuda:0")
 model = ZbufferModelPts(make_opt(), device=dev)
-batch = make_batch(B, 0)
+batch = make_batch(B, [i % 8 for i in range(B)])
 batch = {"images": [t.to(dev) for t in batch["images"]], "cameras": [{k: v.to(dev) for k, v in c.items()} for c in batch["cameras"]]}
 g = torch.Generator().manual_seed(1)
 noise = torch.randn(16, B, 20, generator=g).to(dev)

@@ -426,7 +426,7 @@ def main():
     # beside batch k's refinement decoder (pixelsynth_b200/pipeline.py).  Every step's work is inside the timed region:
     # the loop is drained before the closing event.
     from pixelsynth_b200.pipeline import ViewPipeline
-    pipe = ViewPipeline(model, depth=max(1, args.in_flight), sampler_sms=args.sampler_sms)
+    pipe = ViewPipeline(model, depth=max(1, args.in_flight), sampler_sms=args.sampler_sms, partition="auto")
     pending = []
 
     def step_resident():
@@ -663,7 +663,8 @@ def main():
         "one_step_at_a_time": {"value": views_per_step * args.steps / (ms_serial * 1e-3), "unit": UNIT,
                                "ms_per_step": ms_serial / args.steps,
                                "note": "same model, ZbufferModelPts.forward called serially on the whole device (the latency of a step)"},
-        "sm_partition": {"sampler": n_small, "rest": n_big},
+        "sm_partition": {"sampler": n_small, "rest": n_big} if pipe.sm_counts else
+                        {"unavailable": pipe.partition_error or "one step at a time"},
         "broadcast_ms": bcast_ms,
     }
     if world == 1 and not args.no_cpu_baseline:

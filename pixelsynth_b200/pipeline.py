@@ -27,7 +27,8 @@ from ._lib import check
 class ViewPipeline:
     def __init__(self, model, depth=2, sampler_sms=24, partition=True):
         """model: a ZbufferModelPts.  sampler_sms: size of the sampler's partition (24 of 148 balances the two sides
-        at 64 views per batch).  partition=False keeps plain streams on the whole device."""
+        at 64 views per batch, DESIGN.md section 5).  partition=False keeps plain streams on the whole device;
+        "auto" does so only when the driver cannot create green contexts (`partition_error` says why)."""
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.model, self.depth = model, depth
@@ -35,10 +36,15 @@ class ViewPipeline:
         if self.device.type != "cuda":
             raise RuntimeError("ViewPipeline needs a CUDA device")
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self.sm_counts = None
+        self.sm_counts, self.partition_error = None, None
         if partition and depth > 1:
-            self.sampler_stream, self.streams, self.sm_counts = _partition(index, int(sampler_sms), depth)
-        else:
+            try:
+                self.sampler_stream, self.streams, self.sm_counts = _partition(index, int(sampler_sms), depth)
+            except _lib.PixelSynthB200Error as e:
+                if partition != "auto":
+                    raise
+                self.partition_error = str(e)     # a driver without green contexts: same schedule on plain streams
+        if self.sm_counts is None:
             self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
             self.sampler_stream = torch.cuda.Stream(device=self.device) if depth > 1 else None
         self.slots = []

@@ -329,6 +329,11 @@ void ps_wedge_reset(void);
  * contexts and streams; ps_sm_partition_destroy synchronises and releases them. */
 int ps_sm_partition_create(int device, int small_sms, int n_small_streams, void** small_streams, int n_big_streams,
                            void** big_streams, int* small_count, int* big_count, void** handle);
+/* One more stream on the small (big = 0) or large (big = 1) partition of `handle`; high_priority != 0 gives it the
+ * device's greatest stream priority, so its kernels' CTAs are placed before those of the partition's other streams
+ * whenever SMs free up (the pipeline runs each batch's short front end -- depth net, splat, VQ encoder -- this way, so
+ * the host can build the batch's generation order while the previous batch's decoder still has the partition). */
+int ps_sm_partition_stream(void* handle, int big, int high_priority, void** stream);
 int ps_sm_partition_destroy(void* handle);
 int ps_stream_sm_count(void* stream);
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     "ps_wedge_log": (c_i, [c_p, c_i]),
     "ps_wedge_reset": (None, []),
     "ps_sm_partition_create": (c_i, [c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
+    "ps_sm_partition_stream": (c_i, [c_p, c_i, c_i, c_p]),
     "ps_sm_partition_destroy": (c_i, [c_p]),
     "ps_stream_sm_count": (c_i, [c_p]),
     "ps_launch_count": (ctypes.c_longlong, []),

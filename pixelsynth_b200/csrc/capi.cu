@@ -216,6 +216,22 @@ int ps_sm_partition_create(int device, int small_sms, int n_small_streams, void*
   return PS_OK;
 }
 
+int ps_sm_partition_stream(void* handle, int big, int high_priority, void** stream) {
+  PS_CHECK_ARG(handle && stream);
+  ps::SmPartition* sp = (ps::SmPartition*)handle;
+  CUresult (*stream_create)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  if (!ps::driver_fn("cuGreenCtxStreamCreate", &stream_create))
+    return ps::fail(PS_EUNSUPPORTED, "%s: this driver has no green-context entry points%s", __func__, "");
+  int least = 0, greatest = 0;
+  PS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));  // numerically lower = scheduled first
+  CUstream st = nullptr;
+  if (stream_create(&st, sp->ctx[big ? 1 : 0], CU_STREAM_NON_BLOCKING, high_priority ? greatest : 0) != CUDA_SUCCESS)
+    return ps::fail(PS_ECUDA, "%s: cuGreenCtxStreamCreate failed%s", __func__, "");
+  sp->streams.push_back((cudaStream_t)st);
+  *stream = (void*)st;
+  return PS_OK;
+}
+
 int ps_sm_partition_destroy(void* handle) {
   if (!handle) return PS_OK;
   ps::SmPartition* sp = (ps::SmPartition*)handle;

@@ -88,6 +88,7 @@ class ZbufferModelPts(nn.Module):
         self.ranker = None
         self._bg_pin = None
         self.sampler_stream = None   # optional side stream for the sampler launch (pipelined serving)
+        self.front_stream = None     # optional (high-priority) stream for everything up to the VQ-VAE encoder
 
     # -- z_buffermodel.py:120-184 ---------------------------------------------------------------
     def process_batch(self, batch):
@@ -211,27 +212,34 @@ class ZbufferModelPts(nn.Module):
     # -- z_buffermodel.py:291-419 ---------------------------------------------------------------
     def forward_image(self, batch, netD=None, noise=None, uniforms=None):
         setting = _get(self.opt, "model_setting")
-        if setting in ("train", "gen_paired_img"):
-            K, K_inv, input_RT, input_RTinv, output_RT, output_RTinv, input_img, output_img = self.process_batch(batch)
-            if setting == "train":
-                raise NotImplementedError("training is out of scope (SURVEY.md section 2)")
-        else:
-            K, K_inv, input_RT, input_RTinv, input_img = self.process_batch(batch)
-            output_RTinv, output_RT = self.get_rt_from_rot(_get(self.opt, "direction"), input_RT)
-            output_img = None
-        if _get(self.opt, "use_gt_depth", False):
-            raise NotImplementedError("use_gt_depth: the shipped configuration predicts depth")
-        min_z, max_z = float(_get(self.opt, "min_z")), float(_get(self.opt, "max_z"))
-        if _get(self.opt, "use_inverse_depth", False):
-            raise NotImplementedError("use_inverse_depth is not used by the shipped configuration")
-        regressed_pts = self.pts_regressor.forward(input_img, min_z, max_z)
+        if setting == "train":
+            raise NotImplementedError("training is out of scope (SURVEY.md section 2)")
+        for name, why in (("use_gt_depth", "the shipped configuration predicts depth"),
+                          ("use_inverse_depth", "not used by the shipped configuration")):
+            if _get(self.opt, name, False):
+                raise NotImplementedError(f"{name}: {why}")
         if not _get(self.opt, "use_rgb_features", True):
             raise NotImplementedError("the shipped configuration splats RGB (use_rgb_features)")
-        B = input_img.shape[0]
-        if output_RT.shape[0] != B:
-            output_RT, output_RTinv = output_RT.expand(B, 4, 4), output_RTinv.expand(B, 4, 4)
-        gen_fs, background_mask = self.pts_transformer.forward_justpts(
-            input_img, regressed_pts, K, K_inv, input_RT, input_RTinv, output_RT.contiguous(), output_RTinv.contiguous())
+        # The front end -- everything the host has to wait for before it can build the generation order -- optionally on
+        # its own (high-priority) stream; the rest of the step follows on the caller's stream.
+        cur = torch.cuda.current_stream()
+        front = self.front_stream if self.front_stream is not None else cur
+        if front is not cur:
+            front.wait_stream(cur)
+        with torch.cuda.stream(front):
+            if setting == "gen_paired_img":
+                K, K_inv, input_RT, input_RTinv, output_RT, output_RTinv, input_img, output_img = self.process_batch(batch)
+            else:
+                K, K_inv, input_RT, input_RTinv, input_img = self.process_batch(batch)
+                output_RTinv, output_RT = self.get_rt_from_rot(_get(self.opt, "direction"), input_RT)
+                output_img = None
+            min_z, max_z = float(_get(self.opt, "min_z")), float(_get(self.opt, "max_z"))
+            regressed_pts = self.pts_regressor.forward(input_img, min_z, max_z)
+            B = input_img.shape[0]
+            if output_RT.shape[0] != B:
+                output_RT, output_RTinv = output_RT.expand(B, 4, 4), output_RTinv.expand(B, 4, 4)
+            gen_fs, background_mask = self.pts_transformer.forward_justpts(
+                input_img, regressed_pts, K, K_inv, input_RT, input_RTinv, output_RT.contiguous(), output_RTinv.contiguous())
         if _get(self.opt, "no_outpainting", False):
             raise NotImplementedError("no_outpainting (3-channel decoder, SynSin baseline) is not the shipped configuration")
         else:
@@ -240,10 +248,13 @@ class ZbufferModelPts(nn.Module):
             # encoder is queued, and the host part runs while the GPU encodes.
             if self._bg_pin is None or self._bg_pin.shape != background_mask.shape:
                 self._bg_pin = torch.empty(background_mask.shape, dtype=torch.uint8).pin_memory()
-            self._bg_pin.copy_(background_mask.view(torch.uint8), non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record()
-            codes = self.vqvae.encode_top(gen_fs)
+            with torch.cuda.stream(front):
+                self._bg_pin.copy_(background_mask.view(torch.uint8), non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record()
+                codes = self.vqvae.encode_top(gen_fs)
+            if front is not cur:
+                cur.wait_stream(front)
             ready.synchronize()
             _, order, words, sample_mask = self.get_masks_for_batch(output_RT, input_RTinv, self._bg_pin.numpy())
             prepared = self.outpaint2.prepare(order, words, sample_mask, 0)   # passed explicitly: never reused by a later call

@@ -8,7 +8,10 @@ keeps two batches in flight so that batch k+1's sampler runs beside batch k's de
   * the device's SMs are split into two disjoint CUDA green contexts (ps_sm_partition_create): a small partition for
     every sampler launch, the rest for everything else; persistent kernels size their grids to their partition;
   * batch k runs on stream k % depth of the large partition; its sampler launch is moved to the small partition's
-    stream behind events (ZbufferModelPts.sampler_stream);
+    stream behind events (ZbufferModelPts.sampler_stream); its front end (depth net, splat, VQ encoder: 3 ms of work
+    the host has to wait for before it can build the generation order) runs on a high-priority stream of the large
+    partition (ZbufferModelPts.front_stream), so it is not queued behind the previous batch's decoder and the sampler's
+    partition never waits for the host;
   * the slots are shallow copies of one model: weights, packed plans and the sampler's activation cache are shared
     (sampler launches are serialised on their one stream), per-batch state (pinned mask buffer, `last`) is per slot.
 
@@ -37,9 +40,10 @@ class ViewPipeline:
             raise RuntimeError("ViewPipeline needs a CUDA device")
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.sm_counts, self.partition_error = None, None
+        self.front_streams = [None] * depth
         if partition and depth > 1:
             try:
-                self.sampler_stream, self.streams, self.sm_counts = _partition(index, int(sampler_sms), depth)
+                self.sampler_stream, self.streams, self.front_streams, self.sm_counts = _partition(index, int(sampler_sms), depth)
             except _lib.PixelSynthB200Error as e:
                 if partition != "auto":
                     raise
@@ -47,11 +51,14 @@ class ViewPipeline:
         if self.sm_counts is None:
             self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
             self.sampler_stream = torch.cuda.Stream(device=self.device) if depth > 1 else None
+            if depth > 1:
+                self.front_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(depth)]
         self.slots = []
-        for _ in range(depth):
+        for i in range(depth):
             m = copy.copy(model)          # shares the sub-networks (weights, plans, sampler cache)
             m._bg_pin = None
             m.sampler_stream = self.sampler_stream
+            m.front_stream = self.front_streams[i]
             self.slots.append(m)
         self._events = [None] * depth
         self._pending = {}
@@ -128,18 +135,27 @@ _PARTITIONS = {}
 
 
 def _partition(index, sampler_sms, depth):
+    """-> (sampler stream on the small partition, `depth` streams and `depth` high-priority front-end streams on the
+    large one, (small, large) SM counts)"""
     key = (index, sampler_sms, depth)
     if key not in _PARTITIONS:
         small = (ctypes.c_void_p * 1)()
         big = (ctypes.c_void_p * depth)()
         ns, nb, handle = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_void_p()
         dev = torch.device("cuda", index)
+        L = _lib.lib()
         with torch.cuda.device(index):
             torch.zeros(1, device=dev)  # torch's context first
-            check(_lib.lib().ps_sm_partition_create(index, sampler_sms, 1, small, depth, big, ctypes.byref(ns),
-                                                    ctypes.byref(nb), ctypes.byref(handle)), "ps_sm_partition_create")
+            check(L.ps_sm_partition_create(index, sampler_sms, 1, small, depth, big, ctypes.byref(ns), ctypes.byref(nb),
+                                           ctypes.byref(handle)), "ps_sm_partition_create")
+            front = []
+            for _ in range(depth):
+                st = ctypes.c_void_p()
+                check(L.ps_sm_partition_stream(handle, 1, 1, ctypes.byref(st)), "ps_sm_partition_stream")
+                front.append(torch.cuda.ExternalStream(int(st.value), device=dev))
         _PARTITIONS[key] = (torch.cuda.ExternalStream(int(small[0]), device=dev),
-                            [torch.cuda.ExternalStream(int(big[i]), device=dev) for i in range(depth)], (ns.value, nb.value))
+                            [torch.cuda.ExternalStream(int(big[i]), device=dev) for i in range(depth)], front,
+                            (ns.value, nb.value))
     return _PARTITIONS[key]
 
 

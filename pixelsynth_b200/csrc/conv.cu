@@ -758,6 +758,13 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
   p.stride = d->stride;
   // BN: whole padded Cout when it fits one UMMA (<= 256), else 128-wide column blocks
   int BN = d->cout_pad <= 256 ? d->cout_pad : 128;
+  const int sms = stream_sms((cudaStream_t)stream);  // the whole device, or the stream's green-context partition
+  // few pixels, many channels (the U-Net's bottleneck: 1x1 .. 4x4 images): a handful of CTAs would each stream all the
+  // weights of a wide column block through one SM; narrower column blocks spread that read over more SMs
+  if (!(dbg & 512))
+    while (BN >= 64 && BN % 64 == 0 && d->cout_pad % (BN / 2) == 0 &&
+           p.tiles_x * p.tiles_y * tiles_n * (d->cout_pad / BN) * 2 <= sms)
+      BN /= 2;
   PS_CHECK_ARG(d->cout_pad % BN == 0);
   p.BN = BN;
   // a ring stage carries an A tile only in tap mode (in halo mode every tap of both inputs is read from a halo tile)
@@ -779,7 +786,6 @@ extern "C" int ps_conv_igemm(const ps_conv_desc* d, void* stream) {
     PS_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_dev = dev;
   }
-  const int sms = stream_sms((cudaStream_t)stream);  // the whole device, or the stream's green-context partition
   p.tiles_spatial = p.tiles_x * p.tiles_y * tiles_n;
   p.total_tiles = p.tiles_spatial * (d->cout_pad / BN);
   p.tpg = (halo && BN <= 128 && !(dbg & 1) && p.total_tiles >= 2 * sms) ? 2 : 1;

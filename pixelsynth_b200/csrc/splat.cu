@@ -943,14 +943,26 @@ __global__ void __launch_bounds__(BTH) fine_big_kernel(FineParams q) {
       const int nh = sm.cnt[pix];
       const float xfj = pix_to_ndc(S - 1 - pxi, S), yfj = pix_to_ndc(S - 1 - pyi, S);
       float tcarry = 1.0f, wsum = 0.0f;
-      for (int r = 0; r < rounds; ++r) {
+      // the lane's (up to MAXK / 32) candidates first: independent loads, one memory latency instead of one per round
+      int pp[MAXK / 32];
+      float4 pv[MAXK / 32];
+#pragma unroll
+      for (int r = 0; r < MAXK / 32; ++r) {
+        const int k = r * 32 + lane;
+        pp[r] = (r < rounds && k < nh) ? (int)(unsigned)(A[k][pix] & 0xffffffffull) : -1;
+      }
+#pragma unroll
+      for (int r = 0; r < MAXK / 32; ++r) pv[r] = pp[r] >= 0 ? p4[pp[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < MAXK / 32; ++r) {
+        if (r >= rounds) break;
         const int k = r * 32 + lane;
         const bool valid = k < nh;
         float a = 0.0f, z = -1.0f, d2 = -1.0f;
         int pid = -1;
         if (valid) {
-          const int p = (int)(unsigned)(A[k][pix] & 0xffffffffull);
-          const float4 v = p4[p];
+          const int p = pp[r];
+          const float4 v = pv[r];
           d2 = dist2_rn(__fsub_rn(-v.x, xfj), __fsub_rn(-v.y, yfj));
           z = v.z;
           pid = base + p;

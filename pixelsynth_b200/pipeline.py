@@ -20,6 +20,7 @@ arithmetic depends on the grid size or on what runs beside it.
 """
 import copy
 import ctypes
+import os
 
 import torch
 
@@ -41,6 +42,9 @@ class ViewPipeline:
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.sm_counts, self.partition_error = None, None
         self.front_streams = [None] * depth
+        if partition == "auto" and any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR")):
+            # Nsight Compute cannot profile kernels launched into a green context ("Failed to prepare kernel for profiling")
+            partition, self.partition_error = False, "a profiler is attached (CUDA injection): plain streams"
         if partition and depth > 1:
             try:
                 self.sampler_stream, self.streams, self.front_streams, self.sm_counts = _partition(index, int(sampler_sms), depth)

@@ -136,6 +136,7 @@ struct TcParams {
   int n_chain_body, n_chain_total;
   const ps_lmconv_chunk* chunks_halo;
   short halo_first[33], part_col[33];
+  int halo_group;   // GEMMs per halo tile (host: 4, or 8 on a small SM partition)
   float* part;  // [2 x part_cap rows][LMT_PART_COLS] fp32 partial sums of the halo tiles
   unsigned long long raw_mask;  // bit t: cached tensor t is read through its raw third (by a dilated convolution)
   __half* act;
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lmconv_tc_kernel(const TcParams
         // 16-byte group; group k of row r sits at group k ^ (r & 7) so the epilogue's 16-byte row reads spread over
         // the banks.  Every gather thread passes every use of the two buffers in order (parity waits stay unambiguous).
         const int gg = cur_gemm = ch.gemm;
-        if (!(p.debug & 2048)) wait_progress(prog, tile.h_first + gg / HALO_GROUP, 1, (unsigned int)(gg % HALO_GROUP + 1), tile_index | tkind << 24 | 2 << 28);
+        if (!(p.debug & 2048)) wait_progress(prog, tile.h_first + gg / p.halo_group, 1, (unsigned int)(gg % p.halo_group + 1), tile_index | tkind << 24 | 2 << 28);
         if (!(p.debug & 4096)) mbar_wait(&sm.pempty[gg & 1], ((uint32_t)(gg >> 1) & 1u) ^ 1u);
         const int c0 = p.part_col[gg], ngrp = (p.part_col[gg + 1] - c0) >> 2;
         const int row = t >> 2;
@@ -1497,6 +1498,11 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
   int dev = 0;
   PS_CUDA(cudaGetDevice(&dev));
   const int sms = stream_sms((cudaStream_t)stream);
+  // GEMMs per halo tile: 4 (a 128-row slab of a sampled level spreads over 8 SMs).  Measured on 16- and 24-SM partitions
+  // with 8 and 16: no gain (there the known prefix bounds the launch, not the residency of a level's tiles).
+  int halo_group = HALO_GROUP;
+  if (const char* e = getenv("PS_TC_HALO_GROUP")) halo_group = std::max(2, std::min(32, atoi(e))) & ~1;  // developer aid
+  p.halo_group = halo_group;
   // tiles in level order: a level's rows are split evenly over its tiles
   std::vector<Tile> tiles;
   const int exp_bits = getenv("PS_TC_EXP") ? atoi(getenv("PS_TC_EXP")) : 0;  // developer aid: scheduling experiments
@@ -1517,7 +1523,7 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
     if (split) {
       const int part_base = (int)(((l - first_b_level) & 1) * tc_part_rows(B));
       const int wait = l == first_b_level ? LMT_TENSORS : ((exp_bits & 32) ? PROG_DONE : 0);  // 32: halo tiles do not run ahead
-      const int n_hrow = (rows_l + 127) / 128, n_grp = (32 + HALO_GROUP - 1) / HALO_GROUP;
+      const int n_hrow = (rows_l + 127) / 128, n_grp = (32 + halo_group - 1) / halo_group;
       const int h_first = (int)tiles.size();
       for (int hr = 0; hr < n_hrow; ++hr)
         for (int gr = 0; gr < n_grp; ++gr) {
@@ -1528,7 +1534,7 @@ int ps_lmconv_tc_run(const ps_lmconv_plan* plan, int B, const ps_lmconv_row* row
           tl.prev_first = prev_first;
           tl.prev_count = prev_count;
           tl.wait_start = wait;
-          tl.kind_g = TILE_HALO | (gr * HALO_GROUP) << 8 | std::min(32, (gr + 1) * HALO_GROUP) << 16;
+          tl.kind_g = TILE_HALO | (gr * halo_group) << 8 | std::min(32, (gr + 1) * halo_group) << 16;
           tl.part_row0 = part_base + hr * 128;
           tiles.push_back(tl);
         }

@@ -214,10 +214,10 @@ class ZbufferModelPts(nn.Module):
         setting = _get(self.opt, "model_setting")
         if setting == "train":
             raise NotImplementedError("training is out of scope (SURVEY.md section 2)")
-        for name, why in (("use_gt_depth", "the shipped configuration predicts depth"),
-                          ("use_inverse_depth", "not used by the shipped configuration")):
-            if _get(self.opt, name, False):
-                raise NotImplementedError(f"{name}: {why}")
+        if _get(self.opt, "use_gt_depth", False):
+            # the reference reads an undefined `depth_img` on this branch (z_buffermodel.py:318; its assignment at :164 is
+            # inside a commented-out block), i.e. it raises NameError there
+            raise NotImplementedError("use_gt_depth: dead in the reference too (depth_img is never assigned)")
         if not _get(self.opt, "use_rgb_features", True):
             raise NotImplementedError("the shipped configuration splats RGB (use_rgb_features)")
         # The front end -- everything the host has to wait for before it can build the generation order -- optionally on
@@ -233,8 +233,13 @@ class ZbufferModelPts(nn.Module):
                 K, K_inv, input_RT, input_RTinv, input_img = self.process_batch(batch)
                 output_RTinv, output_RT = self.get_rt_from_rot(_get(self.opt, "direction"), input_RT)
                 output_img = None
-            min_z, max_z = float(_get(self.opt, "min_z")), float(_get(self.opt, "max_z"))
-            regressed_pts = self.pts_regressor.forward(input_img, min_z, max_z)
+            if _get(self.opt, "use_inverse_depth", False):
+                # (:311-315) 1 / (sigmoid(d) * 10 + 0.01): the affine sigmoid is the last convolution's epilogue, the
+                # reciprocal one elementwise pass over the (B,1,S,S) map
+                regressed_pts = torch.reciprocal(self.pts_regressor.forward(input_img, 0.01, 10.01))
+            else:
+                min_z, max_z = float(_get(self.opt, "min_z")), float(_get(self.opt, "max_z"))
+                regressed_pts = self.pts_regressor.forward(input_img, min_z, max_z)
             B = input_img.shape[0]
             if output_RT.shape[0] != B:
                 output_RT, output_RTinv = output_RT.expand(B, 4, 4), output_RTinv.expand(B, 4, 4)

@@ -340,3 +340,24 @@ def test_view_pipeline_two_in_flight_equals_serial(model, partition):
         assert torch.equal(outs[0][1]["PredImg"], want[0])
         t = pipe.submit(jobs[1][0], then=lambda loss, o: (0.5 * o["PredImg"] + 0.5).cpu(), noise=jobs[1][1], uniforms=jobs[1][2])
         assert torch.equal(pipe.result(t), (0.5 * want[1] + 0.5).cpu())
+
+
+def test_use_inverse_depth_option(model):
+    """z_buffermodel.py:311-315: depth = 1 / (sigmoid(Unet(x)) * 10 + 0.01) for long-tailed depth distributions.
+    Against the fp32 oracle U-Net at the depth bar of DESIGN.md section 2, taken on the sigmoid the branch inverts."""
+    from oracle import nets_ref
+    from pixelsynth_b200 import synthetic
+
+    model.opt.use_inverse_depth = True
+    try:
+        batch = make_batch(1)
+        loss, out = model.forward(batch)
+        depth = model.last["depth"].cpu()
+        with torch.no_grad():
+            ref = 1.0 / (torch.sigmoid(nets_ref.unet_features(synthetic.make_state("unet", 0), batch["images"][0])) * 10 + 0.01)
+        assert depth.shape == ref.shape and 0.0999 <= float(depth.min()) and float(depth.max()) <= 100.0
+        sig = lambda d: (1.0 / d - 0.01) / 10                      # back to the sigmoid: the U-Net bar is 1.5 % rms of its range
+        assert float((sig(depth) - sig(ref)).pow(2).mean().sqrt()) <= 0.015 and torch.isfinite(out["PredImg"]).all()
+        assert torch.allclose(out["PredDepthImg"].cpu(), depth / 5 - 1, rtol=1e-6, atol=1e-6)
+    finally:
+        model.opt.use_inverse_depth = False

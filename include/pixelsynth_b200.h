@@ -326,7 +326,8 @@ void ps_wedge_reset(void);
  * and the remainder) and creates n_small_streams / n_big_streams non-blocking streams on them (cudaStream_t, written
  * to the caller's arrays).  Kernels of this library launched on such a stream size their persistent grids to the
  * partition (ps_stream_sm_count).  PS_EUNSUPPORTED when the driver has no green contexts.  The handle owns the
- * contexts and streams; ps_sm_partition_destroy synchronises and releases them. */
+ * contexts and streams; ps_sm_partition_destroy synchronises and releases them.  A handle is not thread-safe: create,
+ * add streams and destroy from one thread (launching on the streams from any thread is fine). */
 int ps_sm_partition_create(int device, int small_sms, int n_small_streams, void** small_streams, int n_big_streams,
                            void** big_streams, int* small_count, int* big_count, void** handle);
 /* One more stream on the small (big = 0) or large (big = 1) partition of `handle`; high_priority != 0 gives it the

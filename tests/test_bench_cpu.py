@@ -33,4 +33,5 @@ def test_flags_and_workload_description():
     cfg = bench.workload_config(a, 8)
     assert "configs[1]" in cfg["workload"] and cfg["views_per_step_per_gpu"] == 64 and cfg["global_views_per_step"] == 512
     assert "(i + r) mod 8" in cfg["view_mix"] and a.view == -1 and a.workload == "views"
+    assert (a.in_flight, a.sampler_sms) == (3, 24) and cfg["in_flight"] == 3 and "24-SM green-context partition" in cfg["schedule"]
     assert bench.BYTES_PER_VIEW_SPLAT_MAPS == 69009408 and bench.BYTES_PER_VIEW_SPLAT_FUSED == 1900544

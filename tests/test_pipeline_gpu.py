@@ -306,8 +306,8 @@ def test_num_samples_ranking_matches_oracle_scores(oracle):
     assert torch.equal(out["PredImg"].cpu(), cands[m.last_best])     # the folded batch equals the per-candidate calls
 
 
-@pytest.mark.parametrize("partition", [True, False])
-def test_view_pipeline_two_in_flight_equals_serial(model, partition):
+@pytest.mark.parametrize("partition,depth", [(True, 2), (False, 2), (True, 3)])
+def test_view_pipeline_two_in_flight_equals_serial(model, partition, depth):
     """pixelsynth_b200.pipeline.ViewPipeline: two batches in flight, the sampler on its own SM partition (CUDA green
     contexts), give bit-identical images to one forward at a time -- five different batches, different views."""
     from pixelsynth_b200 import _lib
@@ -323,13 +323,14 @@ def test_view_pipeline_two_in_flight_equals_serial(model, partition):
     for b, n, u in jobs:
         want.append(model.forward(b, noise=n, uniforms=u)[1]["PredImg"].clone())
     torch.cuda.synchronize()
-    with ViewPipeline(model, depth=2, sampler_sms=24, partition=partition) as pipe:
+    with ViewPipeline(model, depth=depth, sampler_sms=24, partition=partition) as pipe:
         if partition:
             ns, nb = pipe.sm_counts
             assert ns >= 24 and ns + nb == torch.cuda.get_device_properties(0).multi_processor_count
             L = _lib.lib()
             assert L.ps_stream_sm_count(pipe.sampler_stream.cuda_stream) == ns
             assert L.ps_stream_sm_count(pipe.streams[0].cuda_stream) == nb
+            assert L.ps_stream_sm_count(pipe.front_streams[depth - 1].cuda_stream) == nb
             assert L.ps_stream_sm_count(torch.cuda.current_stream().cuda_stream) == ns + nb
         tickets = [pipe.submit(b, noise=n, uniforms=u) for b, n, u in jobs]
         got = [pipe.result(t)[1]["PredImg"] for t in tickets]

@@ -62,7 +62,7 @@ def parse():
                     help="images (= views) per step per GPU (BASELINE configs[3]: batch 64).  The sampler's serial levels "
                          "cost the same at any batch, so throughput grows with it")
     ap.add_argument("--view", type=int, default=-1,
-                    help="-1 (default): image i of rank r renders circle view (i + r) mod 8, so every rank carries the same "
+                    help="-1 (default): slot i of rank r renders circle view (i + r) mod 8 of image (i + r) mod B, so every rank carries the same "
                          "mix of all 8 views; 0..7: every image renders that one view")
     ap.add_argument("--workload", default="views", choices=["views", "scene"],
                     help="views (default, the headline): one novel view per image, BASELINE configs[1]/[3]; scene: BASELINE "
@@ -71,6 +71,7 @@ def parse():
     ap.add_argument("--directions", nargs="+", default=["R", "L"], help="scene sweep directions (scripts/demo_scene.sh uses 10)")
     ap.add_argument("--num_split", type=int, default=2, help="scene sweep splits per direction (scripts/demo_scene.sh: 32)")
     ap.add_argument("--cpu-tokens", type=int, default=16, help="sampler tokens timed per step for the CPU baseline")
+    ap.add_argument("--view-offset", type=int, default=0, help="developer aid: run rank r's view mix on one GPU (offset r)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=3,
                     help="batches in flight per GPU (pixelsynth_b200.pipeline.ViewPipeline); 1 = one forward at a time")
@@ -90,7 +91,8 @@ def make_opt(**kw):
 
 
 def workload_config(args, world):
-    mix = ("image i of rank r renders circle view (i + r) mod 8: every rank carries the same mix of all 8 views"
+    mix = ("slot i of rank r = image (i + r) mod B rendering circle view (i + r) mod 8: every rank carries the same (image, "
+           "view) pairs, rotated"
            if args.view < 0 else "every image renders circle view %d" % args.view)
     return {
         "workload": "BASELINE configs[3] per GPU = configs[1] batched (demo path: depth Unet -> splat -> order/masks -> "
@@ -112,7 +114,7 @@ def workload_config(args, world):
 
 
 def batch_views(args, rank):
-    return [(i + rank) % 8 for i in range(args.batch)] if args.view < 0 else [args.view] * args.batch
+    return [(i + rank + args.view_offset) % 8 for i in range(args.batch)] if args.view < 0 else [args.view] * args.batch
 
 
 def make_batch(B, view, seed=0):
@@ -416,6 +418,13 @@ def main():
         dist.broadcast(warm, 0)
         torch.cuda.synchronize()
     bcast_ms = broadcast_sources(src, world)
+    # rank r holds the SAME (image, view) pairs as rank 0, rotated by r slots (slot i = image (i + r) mod B with view
+    # (i + r) mod 8): every GPU does identical work, so the 1 -> N curve measures the system and not which rank drew the
+    # images with the longest sampling chains (the same pairs in rank order gave 23.9 .. 25.3 ms/step on one GPU)
+    shift = (rank + args.view_offset) % B
+    if shift:
+        src = torch.roll(src, -shift, 0)
+        host_batch["images"] = [torch.roll(t, -shift, 0) for t in host_batch["images"]]
     dev_batch = {"images": [src, src],
                  "cameras": [{k: v.to(dev) for k, v in c.items()} for c in host_batch["cameras"]]}
     g = torch.Generator().manual_seed(1 + rank)

@@ -31,14 +31,20 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   const size_t hw = (size_t)H * W;
   const size_t n = pix / hw, r = pix - n * hw;
   __nv_bfloat16* o = out + pix * cstride;
-  for (int c = 0; c < cstride; ++c) {
-    float v = 0.0f;
-    if (c < C)
-      v = x[(n * C + c) * hw + r];
-    else if (c == C && mask)
-      v = mask[pix] ? 0.0f : 1.0f;
-    o[c] = __float2bfloat16(v);
+  auto value = [&](int c) {
+    if (c < C) return x[(n * C + c) * hw + r];
+    return (c == C && mask) ? (mask[pix] ? 0.0f : 1.0f) : 0.0f;
+  };
+  if ((cstride & 7) == 0 && (((uintptr_t)out) & 15) == 0) {  // one 16-byte store per 8 channels
+    for (int c0 = 0; c0 < cstride; c0 += 8) {
+      __nv_bfloat162 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(value(c0 + 2 * j), value(c0 + 2 * j + 1));
+      *reinterpret_cast<uint4*>(o + c0) = *reinterpret_cast<const uint4*>(h);
+    }
+    return;
   }
+  for (int c = 0; c < cstride; ++c) o[c] = __float2bfloat16(value(c));
 }
 
 struct ResampleOut {

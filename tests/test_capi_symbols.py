@@ -48,6 +48,12 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
                              None) == -1
     assert b"argument check failed" in L.ps_last_error_detail()
     assert L.ps_splat_workspace_bytes(1, 65536, 256, 4.0) > 65536 * 4
+    # SM partitions: argument errors before any driver call; a NULL handle is a no-op to destroy
+    h = ctypes.c_void_p()
+    assert L.ps_sm_partition_create(0, 0, 0, None, 0, None, None, None, ctypes.byref(h)) == -1
+    assert L.ps_sm_partition_create(0, 24, 1, None, 0, None, None, None, ctypes.byref(h)) == -1   # stream array missing
+    assert L.ps_sm_partition_stream(None, 1, 1, ctypes.byref(h)) == -1
+    assert L.ps_sm_partition_destroy(None) == 0
 
 
 def test_ops_refuse_cpu_tensors():
